@@ -1,0 +1,192 @@
+/*
+ * pvn3d_b200.h -- C ABI of libpvn3d_b200.so (hand-written sm_100a kernels).
+ *
+ * This is the drop-in boundary of the PVN3D per-frame keypoint-voting hot path:
+ *   Boundary 1  the nine PointNet++ ops the reference exports from its pybind11 module
+ *               `lib.pointnet2_utils._ext`  (reference: pvn3d/_ext-src/src/bindings.cpp:6-19,
+ *               declarations pvn3d/_ext-src/include/{sampling,ball_query,group_points,interpolate}.h)
+ *   Boundary 2  the post-network vote clustering + pose fit reached through
+ *               MeanShiftTorch.fit          (pvn3d/lib/utils/meanshift_pytorch.py:18-51)
+ *               cal_frame_poses[_lm]        (pvn3d/lib/utils/pvn3d_eval_utils.py:37-110,156-201)
+ *               best_fit_transform          (pvn3d/lib/utils/basic_utils.py:47-80)
+ *
+ * Conventions
+ *   - plain pointers + sizes; no torch / ATen types.  All pointers are DEVICE pointers on the
+ *     current CUDA device unless the name ends in `_host`.
+ *   - tensors are dense, row-major, float32 / int32, batch-major -- exactly the layouts the
+ *     reference ops take (AT_CHECK contiguity, pvn3d/_ext-src/include/utils.h:5-25).
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it, never
+ *     synchronises, keeps no global state and is re-entrant (reference: launches on
+ *     at::cuda::getCurrentCUDAStream(), e.g. ball_query_gpu.cu:49).
+ *   - outputs are fully written by the callee (the reference zero-fills them with torch::zeros
+ *     first; rows the reference leaves at zero are written as zero here).
+ *   - return value: 0 = PVN3D_OK, negative = error code (pvn3d_strerror()).  The library never
+ *     calls exit() (the reference does: pvn3d/_ext-src/include/cuda_utils.h:30-39).
+ */
+#ifndef PVN3D_B200_H
+#define PVN3D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PVN3D_OK 0
+#define PVN3D_ERR_INVALID_ARG (-1)   /* null pointer / negative or inconsistent size            */
+#define PVN3D_ERR_UNSUPPORTED (-2)   /* size outside what the kernels are built for             */
+#define PVN3D_ERR_CUDA (-3)          /* a CUDA runtime call / launch failed (cudaGetLastError)  */
+#define PVN3D_ERR_WORKSPACE (-4)     /* caller-provided workspace too small                     */
+
+typedef void *pvn3d_stream_t; /* cudaStream_t */
+
+int pvn3d_version(void);                 /* ABI version, currently 1                         */
+const char *pvn3d_strerror(int code);    /* static string                                    */
+const char *pvn3d_last_cuda_error(void); /* thread-local text of the last PVN3D_ERR_CUDA     */
+int pvn3d_device_sm_count(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ------------------------------------------------------------------------------------------
+ * Boundary 1: lib.pointnet2_utils._ext
+ * ---------------------------------------------------------------------------------------- */
+
+/* furthest_point_sampling(points[B,N,3], nsamples) -> idx[B,nsamples] int32
+ * replaces sampling.h:6 / sampling.cpp:65-86 / sampling_gpu.cu:69-229.
+ * Bit-exact with the reference, including its tie-break (512-thread strided ownership +
+ * shared-memory tree whose ties go to the lower tree slot) and the |p|^2 <= 1e-3 skip rule.
+ * No [B,N] scratch tensor is needed (running min-distances live in registers). */
+int pvn3d_furthest_point_sampling(const float *xyz, int b, int n, int m, int *idx,
+                                  pvn3d_stream_t stream);
+
+/* gather_points(points[B,C,N], idx[B,M]) -> out[B,C,M]        (sampling.h:4, sampling_gpu.cu:8-30) */
+int pvn3d_gather_points(const float *points, const int *idx, int b, int c, int n, int m,
+                        float *out, pvn3d_stream_t stream);
+/* gather_points_grad(grad_out[B,C,M], idx[B,M], N) -> grad_points[B,C,N]  (sampling_gpu.cu:34-57);
+ * grad_points is zero-filled by the callee, then scatter-added. */
+int pvn3d_gather_points_grad(const float *grad_out, const int *idx, int b, int c, int n, int m,
+                             float *grad_points, pvn3d_stream_t stream);
+
+/* ball_query(new_xyz[B,M,3], xyz[B,N,3], radius, nsample) -> idx[B,M,nsample] int32
+ * replaces ball_query.h:4-5 / ball_query_gpu.cu:9-54: first `nsample` indices in ascending
+ * order with d2 < radius^2 (strict), first hit pre-fills the row, empty ball -> zeros.
+ * d2 is evaluated as fma(dz,dz,fma(dx,dx,dy*dy)) like the reference SASS => bit-exact idx. */
+int pvn3d_ball_query(const float *new_xyz, const float *xyz, int b, int n, int m, float radius,
+                     int nsample, int *idx, pvn3d_stream_t stream);
+
+/* group_points(points[B,C,N], idx[B,M,S]) -> out[B,C,M,S]       (group_points_gpu.cu:8-39) */
+int pvn3d_group_points(const float *points, const int *idx, int b, int c, int n, int npoints,
+                       int nsample, float *out, pvn3d_stream_t stream);
+/* group_points_grad(grad_out[B,C,M,S], idx[B,M,S], N) -> grad_points[B,C,N]  (:43-75) */
+int pvn3d_group_points_grad(const float *grad_out, const int *idx, int b, int c, int n,
+                            int npoints, int nsample, float *grad_points, pvn3d_stream_t stream);
+
+/* three_nn(unknown[B,n,3], known[B,m,3]) -> dist2[B,n,3] f32 (SQUARED), idx[B,n,3] i32
+ * replaces interpolate.h:6 / interpolate_gpu.cu:9-68: ascending d2, strict '<' cascade
+ * (first index wins ties); unused slots when m < 3 hold +inf / 0. */
+int pvn3d_three_nn(const float *unknown, const float *known, int b, int n, int m, float *dist2,
+                   int *idx, pvn3d_stream_t stream);
+
+/* three_interpolate(points[B,C,M], idx[B,N,3], weight[B,N,3]) -> out[B,C,N]
+ * (interpolate_gpu.cu:72-111); sum order p1*w1 + p2*w2 + p3*w3 contracted as the reference
+ * SASS does (fmul, fma, fma) => bit-exact. */
+int pvn3d_three_interpolate(const float *points, const int *idx, const float *weight, int b, int c,
+                            int m, int n, float *out, pvn3d_stream_t stream);
+/* three_interpolate_grad(grad_out[B,C,N], idx, weight, M) -> grad_points[B,C,M].
+ * NOTE: implements the mathematically correct scatter of interpolate_gpu.cu:116-143; the
+ * reference host wrapper launches the forward kernel by mistake (interpolate.cpp:89-93). */
+int pvn3d_three_interpolate_grad(const float *grad_out, const int *idx, const float *weight, int b,
+                                 int c, int n, int m, float *grad_points, pvn3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused forms of the same path (what QueryAndGroup.forward / PointnetFPModule.forward compose
+ * from the ops above: pointnet2_utils.py:293-330, pointnet2_modules.py:183-190).
+ * ---------------------------------------------------------------------------------------- */
+
+/* channel-major [B,C,N] <-> point-major [B,N,C] (staging layout of the fused kernels) */
+int pvn3d_transpose_cn_to_nc(const float *src_bcn, int b, int c, int n, float *dst_bnc,
+                             pvn3d_stream_t stream);
+int pvn3d_transpose_nc_to_cn(const float *src_bnc, int b, int n, int c, float *dst_bcn,
+                             pvn3d_stream_t stream);
+
+/* query_and_group: ball_query + group(xyz) - centre + group(features) + concat in ONE kernel.
+ *   xyz[B,N,3], new_xyz[B,M,3], feat_pm[B,N,ldf] point-major rows whose first C columns are the
+ *   descriptors (ldf >= C; C may be 0 -> feat_pm NULL)
+ *   -> idx[B,M,S] (may be NULL), out[B,3+C,M,S]   == QueryAndGroup(radius,S,use_xyz=True).forward
+ * idx bit-exact with pvn3d_ball_query; out bit-exact with the composed reference ops.
+ * Supported: 1 <= S <= 256 (larger S: compose pvn3d_ball_query + pvn3d_group_points). */
+int pvn3d_query_and_group(const float *xyz, const float *new_xyz, const float *feat_pm, int ldf,
+                          int b, int n, int m, int c, float radius, int nsample, int *idx,
+                          float *out, pvn3d_stream_t stream);
+
+/* three_nn + (1/(sqrt(d2)+1e-8) normalised) weights + three_interpolate, point-major features:
+ *   unknown[B,n,3], known[B,m,3], known_feat_pm[B,m,C] -> out_pm[B,n,ldo] columns [col0,col0+C)
+ *   (ldo >= col0+C lets the caller interpolate straight into the concat buffer of the FP module),
+ *   optionally also dist2[B,n,3], idx[B,n,3] (NULL to skip).
+ * Weights follow pointnet2_modules.py:184-186 in fp32 (sqrt.rn, div.rn). */
+int pvn3d_three_nn_interpolate(const float *unknown, const float *known, const float *known_feat_pm,
+                               int b, int n, int m, int c, float *out_pm, int ldo, int col0,
+                               float *dist2, int *idx, pvn3d_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Boundary 2: MeanShiftTorch.fit, cal_frame_poses / cal_frame_poses_lm, best_fit_transform
+ * ---------------------------------------------------------------------------------------- */
+
+/* Flags for the mean-shift iteration */
+#define PVN3D_MS_STRICT 0u      /* iterate every seed until the reference's global stop rule   */
+#define PVN3D_MS_EARLY_EXIT 1u  /* additionally stop a fit once the RETURNED seed is stationary */
+
+/* A batch of F independent MeanShiftTorch(bandwidth, max_iter).fit(A_f) problems.
+ *   pts        [cap,4] f32  vote clouds (x,y,z,unused); fit f owns rows
+ *                           [fit_start[f], fit_start[f]+fit_count[f])  (segments may have gaps)
+ *   fit_start  [F] i32, fit_count [F] i32   (device; count 0 = empty fit: outputs zeroed)
+ *   n_fits     F
+ *   cap        number of float4 rows addressable in pts / labels / workspace
+ *   bandwidth  double, as the Python float the reference holds: the fp32 thresholds
+ *              float(bandwidth) and float(bandwidth*1e-3) are derived from it exactly as torch
+ *              does when a float32 tensor is compared with a Python scalar.
+ * outputs
+ *   ctr      [F,4]  f32   C[max_idx] (x,y,z) and the iteration count as float in .w
+ *   labels   [cap]   u8   1 where |A[max_idx]-A_j| < bandwidth, indexed like pts (NULL to skip)
+ *   max_idx  [F]    i32   first index (within the fit) of the densest input point
+ *   n_in     [F]    i32   its inlier count
+ * workspace: pvn3d_meanshift_workspace_bytes(cap, n_fits) bytes, 256-B aligned.
+ * Semantics follow meanshift_pytorch.py:24-51 (stop when max_i |dC_i| < bandwidth*1e-3 or
+ * it > max_iter; densest *input* point selects the returned seed; first-index arg-max). */
+size_t pvn3d_meanshift_workspace_bytes(int cap, int n_fits);
+int pvn3d_meanshift_fit_batch(const float *pts, const int *fit_start, const int *fit_count,
+                              int n_fits, int cap, double bandwidth, int max_iter, unsigned flags,
+                              float *ctr, uint8_t *labels, int *max_idx, int *n_in,
+                              void *workspace, size_t workspace_bytes, pvn3d_stream_t stream);
+
+/* best_fit_transform(A[P,3], B[P,3]) for a batch: least-squares rigid fit A -> B (Kabsch, SVD
+ * with reflection fix), basic_utils.py:47-80.  valid[i]==0 -> identity(3x4) (reference:
+ * pvn3d_eval_utils.py:79-81).  Computation in float64 on device from float32 inputs.
+ *   a[nfit,P,3], b[nfit,P,3], valid[nfit] (NULL = all valid) -> rt[nfit,3,4] f32 */
+int pvn3d_best_fit_transform_batch(const float *a, const float *b, const uint8_t *valid, int nfit,
+                                   int p, float *rt, pvn3d_stream_t stream);
+
+/* cal_frame_poses / cal_frame_poses_lm for a batch of frames, fully on device, no host sync.
+ *   pcld   [B,N,3] f32, mask [B,N] i32 (class id per point, 0 = background),
+ *   ctr_of [B,N,3] f32 (reference ctr_of[0]), kp_of [B,K,N,3] f32
+ *   mesh_kps [n_cls,K+1,3] f32  object-frame keypoints, centre LAST (pvn3d_eval_utils.py:99-103);
+ *            row 0 unused.  LineMOD: n_cls=2 and row 1 = fixtures of obj_id.
+ *   cls_radius [n_cls] f32   float32(r*0.8) thresholds of the centre-cluster filter
+ *            (pvn3d_eval_utils.py:69), row 0 unused; NULL when use_ctr_clus_flter==0.
+ * outputs
+ *   poses    [B,n_cls,3,4] f32   identity for classes that are absent or lost all points
+ *   present  [B,n_cls] u8        1 where the class id was in np.unique(mask[mask>0])  (:50)
+ *   cls_kps  [B,n_cls,K+1,3] f32 voted keypoints + centre (NULL to skip)
+ *   new_mask [B,N] i32           relabelled mask of the filter pass (NULL to skip)        (:66-72)
+ * use_ctr must be 1 (the reference's use_ctr=False branch is never exercised: SURVEY App. A.5). */
+size_t pvn3d_frame_poses_workspace_bytes(int b, int n, int k, int n_cls);
+int pvn3d_frame_poses_batch(const float *pcld, const int *mask, const float *ctr_of,
+                            const float *kp_of, int b, int n, int k, int n_cls,
+                            const float *mesh_kps, const float *cls_radius, int use_ctr_clus_flter,
+                            double bandwidth, int max_iter, unsigned ms_flags, float *poses,
+                            uint8_t *present, float *cls_kps, int *new_mask, void *workspace,
+                            size_t workspace_bytes, pvn3d_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PVN3D_B200_H */

@@ -1,0 +1,103 @@
+"""ctypes binding of libpvn3d_b200.so -- the only way Python reaches the kernels.
+
+The library is the product: if it is missing or cannot be loaded this module raises, and every
+op built on it raises with it.  There is no PyTorch / CPU fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_size_t, c_uint, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpvn3d_b200.so")
+
+PVN3D_MS_STRICT = 0
+PVN3D_MS_EARLY_EXIT = 1
+
+_ERR_NAMES = {-1: "invalid argument", -2: "unsupported size", -3: "CUDA error", -4: "workspace too small"}
+
+# name -> (restype, argtypes); mirrors include/pvn3d_b200.h one to one
+_P = c_void_p
+_SIGNATURES = {
+    "pvn3d_version": (c_int, []),
+    "pvn3d_strerror": (c_char_p, [c_int]),
+    "pvn3d_last_cuda_error": (c_char_p, []),
+    "pvn3d_device_sm_count": (c_int, [_P, _P, _P]),
+    "pvn3d_furthest_point_sampling": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
+    "pvn3d_gather_points": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "pvn3d_gather_points_grad": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "pvn3d_ball_query": (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_int, _P, _P]),
+    "pvn3d_group_points": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "pvn3d_group_points_grad": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "pvn3d_three_nn": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P, _P]),
+    "pvn3d_three_interpolate": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "pvn3d_three_interpolate_grad": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "pvn3d_transpose_cn_to_nc": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
+    "pvn3d_transpose_nc_to_cn": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
+    "pvn3d_query_and_group": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _P, _P, _P]),
+    "pvn3d_three_nn_interpolate": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, _P]),
+    "pvn3d_meanshift_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "pvn3d_meanshift_fit_batch": (c_int, [_P, _P, _P, c_int, c_int, c_double, c_int, c_uint, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "pvn3d_best_fit_transform_batch": (c_int, [_P, _P, _P, c_int, c_int, _P, _P]),
+    "pvn3d_frame_poses_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "pvn3d_frame_poses_batch": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_double, c_int, c_uint, _P, _P, _P, _P, _P, c_size_t, _P]),
+}
+# optional entry points (later build stages); bound when present
+_OPTIONAL = {
+    "pvn3d_mlp_workspace_bytes",
+    "pvn3d_sa_mlp_forward",
+    "pvn3d_fp_mlp_forward",
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+class Pvn3dError(RuntimeError):
+    pass
+
+
+def load() -> ctypes.CDLL:
+    """dlopen the kernel library (once).  Raises Pvn3dError when it is absent: build it with
+    `python -m pvn3d_b200.build` (or __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Pvn3dError(
+            f"{LIB_PATH} not found: the sm_100a kernel library is not built "
+            "(run `python -m pvn3d_b200.build`); pvn3d_b200 has no CPU / PyTorch fallback")
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as e:  # pragma: no cover
+        raise Pvn3dError(f"cannot load {LIB_PATH}: {e}") from e
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc == 0:
+        return
+    lib = load()
+    msg = _ERR_NAMES.get(rc, f"error {rc}")
+    if rc == -3:
+        detail = lib.pvn3d_last_cuda_error()
+        msg += f": {detail.decode() if detail else '?'}"
+    raise Pvn3dError(f"{what}: {msg}")
+
+
+def ptr(t) -> int:
+    """device/host address of a torch tensor (0 for None)"""
+    return 0 if t is None else t.data_ptr()
+
+
+def stream_ptr(device=None) -> int:
+    import torch
+
+    return torch.cuda.current_stream(device).cuda_stream

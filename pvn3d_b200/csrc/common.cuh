@@ -1,0 +1,153 @@
+// common.cuh -- shared helpers for the sm_100a kernels of libpvn3d_b200.so
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "pvn3d_b200.h"
+
+namespace pvn3d {
+
+// ---- host-side error plumbing (never exit(); reference cuda_utils.h:30-39 does) -------------
+void note_cuda_error(cudaError_t e, const char *where);
+static inline int check_launch(const char *where) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    note_cuda_error(e, where);
+    return PVN3D_ERR_CUDA;
+  }
+  return PVN3D_OK;
+}
+#define PVN3D_CUDA_TRY(expr, where)      \
+  do {                                   \
+    cudaError_t _e = (expr);             \
+    if (_e != cudaSuccess) {             \
+      ::pvn3d::note_cuda_error(_e, where); \
+      return PVN3D_ERR_CUDA;             \
+    }                                    \
+  } while (0)
+
+int sm_count();  // cached per process (device of first call)
+
+// "do this once per device" latch for cudaFuncSetAttribute-style setup (function attributes are
+// per context, and nn.DataParallel-style callers drive several devices from one process).
+struct PerDeviceOnce {
+  unsigned long long mask = 0ull;
+  bool first_time() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    const unsigned long long bit = 1ull << dev;
+    const unsigned long long old = __atomic_fetch_or(&mask, bit, __ATOMIC_RELAXED);
+    return (old & bit) == 0ull;
+  }
+};
+
+static inline cudaStream_t as_stream(pvn3d_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Same arithmetic as the reference launch helper opt_n_threads (cuda_utils.h:15-19): the block
+// size decides the FPS tie-break, so it is reproduced with the identical double-precision
+// log ratio and truncation.
+int ref_opt_n_threads(int work_size);
+
+#ifdef __CUDACC__
+// ---- device helpers ---------------------------------------------------------------------------
+
+// Squared distance exactly as nvcc contracts the reference expression
+//   (ax-bx)*(ax-bx) + (ay-by)*(ay-by) + (az-bz)*(az-bz)
+// in ball_query_gpu.cu:31-32, sampling_gpu.cu:103-104, interpolate_gpu.cu:33 (SASS checked on
+// the oracle build: FMUL dy,dy ; FFMA dx,dx ; FFMA dz,dz).
+__device__ __forceinline__ float ref_sqdist(float dx, float dy, float dz) {
+  return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+// torch.norm(v, dim=-1)^2 on CPU float32 == fma(z,z,fma(y,y,x*x))  (re-probed
+// by oracle/probe_torch_norm.py): the order used for every *exact* (label / count) decision of the
+// mean-shift path.
+__device__ __forceinline__ float torch_sqnorm(float dx, float dy, float dz) {
+  return __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+}
+
+__device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ unsigned lanemask_lt() {
+  unsigned m;
+  asm volatile("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ---- mbarrier + 1-D bulk (TMA engine) copies: global -> shared ---------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// bytes must be a multiple of 16, src/dst 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, unsigned bytes,
+                                         uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// Stage `count` points (3 floats each) starting at point `first` of one cloud into shared memory.
+// Fast path: one 1-D bulk copy issued by thread 0, completion on an mbarrier.
+__device__ __forceinline__ void stage_xyz_tile(float *s_tile, const float *cloud, int first,
+                                               int count, uint64_t *bar, unsigned &phase,
+                                               bool bulk_ok) {
+  const float *src = cloud + static_cast<size_t>(first) * 3;
+  const unsigned bytes = static_cast<unsigned>(count) * 12u;
+  if (bulk_ok && (bytes & 15u) == 0u && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0u)) {
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(s_tile, src, bytes, bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1u;
+  } else {
+    for (int i = threadIdx.x; i < count * 3; i += blockDim.x) s_tile[i] = __ldg(src + i);
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ float ldg_stream(const float *p) {
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg_stream(float *p, float v) {
+  asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void stg_stream4(float *p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+#endif  // __CUDACC__
+
+}  // namespace pvn3d

@@ -1,0 +1,510 @@
+// meanshift.cu -- batched Gaussian mean-shift vote clustering for sm_100a.
+//
+// Replaces MeanShiftTorch.fit (reference pvn3d/lib/utils/meanshift_pytorch.py:13-51), which per
+// iteration materialises four [n,n,3] float32 tensors with ~10 torch kernels and one host sync,
+// and is called 1 + 1 + 8 times per object from a Python loop (pvn3d_eval_utils.py:53-57,84-97).
+// Here ANY number of fits (every class of every frame, all keypoints) runs in four launches:
+//
+//   ms_setup     per-fit bookkeeping, tile prefix sums
+//   ms_density   exact pass: num_in_i = #{j : |A_i - A_j| < bw}; arg-max with first-index ties
+//                -> max_idx (meanshift_pytorch.py:46-49).  Distances use the fp32 contraction CPU
+//                torch.norm uses (common.cuh: torch_sqnorm) and a pre-computed d^2 threshold that
+//                is equivalent to `sqrtf(d2) < float(bw)`, so labels / counts are bit-exact.
+//   ms_prepare   labels = |A[max_idx] - A_j| < bw (:50), origin = A[max_idx], centred copies
+//   ms_iterate   ONE persistent cooperative kernel runs every iteration of every fit:
+//                work items (fit, tile of seeds) are handed out by an atomic ticket, all seeds
+//                of a tile sweep the fit's points from shared memory (broadcast LDS.128), and a
+//                grid barrier per iteration applies the reference's GLOBAL stop rule per fit
+//                (max_i |dC_i| < bw*1e-3 or it > max_iter, :39-42).  No host involvement.
+//
+// Arithmetic of the sweep: with points/seeds centred on A[max_idx] (a', c') and
+// k = -log2(e)/(2 bw^2):  w_ij = 2^( k|a'|^2 + k|c'|^2 - 2k a'.c' )  -- 1 FADD + 3 FFMA + 1 MUFU.EX2
+// per pair, then 1 FADD + 3 FFMA to accumulate sum(w), sum(w a').  The reference's constant
+// 1/(bw sqrt(2 pi)) cancels in sum(w a)/sum(w).  Centres agree with the
+// CPU reference to ~1e-6 relative (tests pin 1e-4, BASELINE.json north_star); labels, counts and
+// max_idx are exact.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace pvn3d {
+namespace {
+
+constexpr int kMsThreads = 256;
+constexpr int kMsFitMax = 4096;  // fits per launch chunk (prefix array lives in shared memory)
+constexpr int kMsPtTile = 1024;  // points per shared-memory tile (16 KB)
+constexpr int kMsWarps = kMsThreads / 32;
+
+struct MsArgs {
+  const float4 *pts;
+  const int *fit_start;
+  const int *fit_count;
+  int n_fits;
+  float t2;           // d2 < t2  <=>  sqrtf(d2) < float(bandwidth)
+  float stop_thresh;  // float(bandwidth * 1e-3)
+  float eps_stat;     // early-exit stationarity threshold for the returned seed
+  float kexp;         // -log2(e) / (2 bw^2)
+  int max_iter;
+  unsigned flags;
+  // outputs
+  float4 *ctr;
+  uint8_t *labels;
+  int *max_idx;
+  int *n_in;
+  // workspace
+  float4 *cpts;
+  float4 *seeds;
+  unsigned long long *best_key;
+  unsigned *fitmax;  // [3][n_fits]
+  int *done;
+  int *iters;
+  float *star_shift;  // [2][n_fits] shift of the returned seed, double-buffered by iteration parity
+  int *dens_prefix;  // [n_fits+1]
+  int *cfg;          // [0..2] tickets, [3] R (seeds per thread), [4] total points
+  int grid_ctas;     // CTAs of the persistent kernel (for the R heuristic)
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// exclusive scan of one int per thread across the CTA; returns the exclusive prefix, *total = sum
+template <int NT>
+__device__ __forceinline__ int block_exclusive_scan(int v, int *s_warp /*[NT/32]*/, int *total) {
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  int wsum = (lane < NT / 32) ? s_warp[lane] : 0;
+  int wincl = wsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, wincl, o);
+    if (lane >= o) wincl += u;
+  }
+  const int wexcl = __shfl_sync(0xffffffffu, wincl - wsum, warp);
+  *total = __shfl_sync(0xffffffffu, wincl, NT / 32 - 1);
+  __syncthreads();  // s_warp reusable
+  return wexcl + incl - v;
+}
+
+// largest f in [0, n) with prefix[f] <= x   (prefix non-decreasing, prefix[0] = 0 <= x)
+__device__ __forceinline__ int find_segment(const int *prefix, int n, int x) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (prefix[mid] <= x) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) ms_setup_kernel(MsArgs a) {
+  __shared__ int s_warp[32];
+  __shared__ int s_run;
+  const int t = threadIdx.x;
+  if (t == 0) s_run = 0;
+  __syncthreads();
+  long long pts_total = 0;
+  for (int f0 = 0; f0 < a.n_fits; f0 += 1024) {
+    const int f = f0 + t;
+    int cnt = 0;
+    if (f < a.n_fits) {
+      cnt = max(a.fit_count[f], 0);
+      a.best_key[f] = 0ull;
+      a.fitmax[f] = a.fitmax[a.n_fits + f] = a.fitmax[2 * a.n_fits + f] = 0u;
+      a.done[f] = cnt == 0;
+      a.iters[f] = 0;
+      a.star_shift[f] = a.star_shift[a.n_fits + f] = __int_as_float(0x7f800000);
+      if (cnt == 0) {
+        a.ctr[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+        a.max_idx[f] = 0;
+        a.n_in[f] = 0;
+      }
+    }
+    int total;
+    const int excl = block_exclusive_scan<1024>((cnt + kMsThreads - 1) / kMsThreads, s_warp, &total);
+    const int run = s_run;
+    if (f < a.n_fits) a.dens_prefix[f] = run + excl;
+    int ptot;
+    (void)block_exclusive_scan<1024>(cnt, s_warp, &ptot);
+    pts_total += ptot;
+    __syncthreads();
+    if (t == 0) s_run = run + total;
+    __syncthreads();
+  }
+  if (t == 0) {
+    a.dens_prefix[a.n_fits] = s_run;
+    a.cfg[0] = a.cfg[1] = a.cfg[2] = 0;
+    // seeds per thread: the largest R that still leaves >= 3 tiles per CTA of the persistent grid
+    const long long want = 3ll * a.grid_ctas;
+    int r = 4;
+    while (r > 1 && pts_total / (kMsThreads * r) < want) r >>= 1;
+    a.cfg[3] = r;
+    a.cfg[4] = static_cast<int>(pts_total > 0x7fffffffll ? 0x7fffffffll : pts_total);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// exact density pass: one thread per input point, all points of the fit swept from shared memory
+__global__ void __launch_bounds__(kMsThreads) ms_density_kernel(MsArgs a) {
+  __shared__ float4 s_pts[kMsPtTile];
+  __shared__ unsigned long long s_key[kMsWarps];
+  const int tile = blockIdx.x;
+  if (tile >= a.dens_prefix[a.n_fits]) return;
+  const int f = find_segment(a.dens_prefix, a.n_fits, tile);
+  const int start = a.fit_start[f], cnt = a.fit_count[f];
+  const int i = (tile - a.dens_prefix[f]) * kMsThreads + threadIdx.x;
+  const bool live = i < cnt;
+  const float4 me = a.pts[start + (live ? i : 0)];
+  const float t2 = a.t2;
+  int count = 0;
+  for (int base = 0; base < cnt; base += kMsPtTile) {
+    const int n = min(kMsPtTile, cnt - base);
+    __syncthreads();
+    for (int q = threadIdx.x; q < n; q += kMsThreads) s_pts[q] = a.pts[start + base + q];
+    __syncthreads();
+#pragma unroll 8
+    for (int j = 0; j < n; ++j) {
+      const float4 p = s_pts[j];
+      // dis = torch.norm(Ar - Cr): diff = A_j - A_i   (meanshift_pytorch.py:46-48)
+      count += torch_sqnorm(p.x - me.x, p.y - me.y, p.z - me.z) < t2 ? 1 : 0;
+    }
+  }
+  unsigned long long key =
+      live ? ((static_cast<unsigned long long>(count) << 32) | (0xFFFFFFFFu - static_cast<unsigned>(i)))
+           : 0ull;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+    key = other > key ? other : key;
+  }
+  if ((threadIdx.x & 31) == 0) s_key[threadIdx.x >> 5] = key;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < kMsWarps; ++w) key = s_key[w] > key ? s_key[w] : key;
+    atomicMax(a.best_key + f, key);  // (count desc, index asc): torch.max first-index rule (:49)
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kMsThreads) ms_prepare_kernel(MsArgs a) {
+  const int tile = blockIdx.x;
+  if (tile >= a.dens_prefix[a.n_fits]) return;
+  const int f = find_segment(a.dens_prefix, a.n_fits, tile);
+  const int start = a.fit_start[f], cnt = a.fit_count[f];
+  const int i = (tile - a.dens_prefix[f]) * kMsThreads + threadIdx.x;
+  const unsigned long long key = a.best_key[f];
+  const int mi = static_cast<int>(0xFFFFFFFFu - static_cast<unsigned>(key & 0xFFFFFFFFull));
+  if (i == 0) {
+    a.max_idx[f] = mi;
+    a.n_in[f] = static_cast<int>(key >> 32);
+  }
+  if (i >= cnt) return;
+  const float4 o = a.pts[start + mi];
+  const float4 p = a.pts[start + i];
+  const float dx = p.x - o.x, dy = p.y - o.y, dz = p.z - o.z;
+  if (a.labels) a.labels[start + i] = torch_sqnorm(dx, dy, dz) < a.t2 ? 1 : 0;  // (:50)
+  a.cpts[start + i] = make_float4(dx, dy, dz, a.kexp * (dx * dx + dy * dy + dz * dz));
+  a.seeds[start + i] = make_float4(dx, dy, dz, 0.f);  // C <- A.clone()  (:31)
+}
+
+// ------------------------------------------------------------------------------------------------
+// one tile of seeds (256*R) of fit f sweeps all of the fit's centred points; returns through
+// atomicMax the tile's largest shift for iteration slot `slot`
+template <int R>
+__device__ __forceinline__ void ms_process_tile(const MsArgs &a, int f, int tile_in_fit, int slot,
+                                                int parity, float4 *s_pts, float *s_red) {
+  const int start = a.fit_start[f], cnt = a.fit_count[f];
+  const int t = threadIdx.x;
+  const float k = a.kexp;
+  float qx[R], qy[R], qz[R], qw[R];
+  float sw[R], sx[R], sy[R], sz[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i = tile_in_fit * (kMsThreads * R) + r * kMsThreads + t;
+    const float4 c = a.seeds[start + (i < cnt ? i : 0)];
+    qx[r] = -2.f * k * c.x;
+    qy[r] = -2.f * k * c.y;
+    qz[r] = -2.f * k * c.z;
+    qw[r] = k * (c.x * c.x + c.y * c.y + c.z * c.z);
+    sw[r] = sx[r] = sy[r] = sz[r] = 0.f;
+  }
+  for (int base = 0; base < cnt; base += kMsPtTile) {
+    const int n = min(kMsPtTile, cnt - base);
+    __syncthreads();
+    for (int q = t; q < n; q += kMsThreads) s_pts[q] = a.cpts[start + base + q];
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < n; ++j) {
+      const float4 p = s_pts[j];  // broadcast
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float e = fmaf(p.x, qx[r], fmaf(p.y, qy[r], fmaf(p.z, qz[r], p.w + qw[r])));
+        const float w = ex2_approx(e);
+        sw[r] += w;
+        sx[r] = fmaf(w, p.x, sx[r]);
+        sy[r] = fmaf(w, p.y, sy[r]);
+        sz[r] = fmaf(w, p.z, sz[r]);
+      }
+    }
+  }
+  float mshift = 0.f;
+  const int star = a.max_idx[f];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int i = tile_in_fit * (kMsThreads * R) + r * kMsThreads + t;
+    if (i < cnt) {
+      // new_C = sum(w*A)/sum(w); Adis = |new_C - C|   (meanshift_pytorch.py:37-38)
+      const float nx = __fdiv_rn(sx[r], sw[r]), ny = __fdiv_rn(sy[r], sw[r]),
+                  nz = __fdiv_rn(sz[r], sw[r]);
+      const float4 c = a.seeds[start + i];  // old C (re-read: keeps the sweep's register set small)
+      const float sh = __fsqrt_rn(torch_sqnorm(nx - c.x, ny - c.y, nz - c.z));
+      a.seeds[start + i] = make_float4(nx, ny, nz, sh);
+      mshift = fmaxf(mshift, sh);
+      if (i == star) a.star_shift[static_cast<size_t>(parity) * a.n_fits + f] = sh;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mshift = fmaxf(mshift, __shfl_xor_sync(0xffffffffu, mshift, o));
+  if ((t & 31) == 0) s_red[t >> 5] = mshift;
+  __syncthreads();
+  if (t == 0) {
+#pragma unroll
+    for (int w = 1; w < kMsWarps; ++w) mshift = fmaxf(mshift, s_red[w]);
+    atomicMax(a.fitmax + static_cast<size_t>(slot) * a.n_fits + f, __float_as_uint(mshift));
+  }
+}
+
+struct MsIterSmem {
+  int prefix[kMsFitMax + 1];
+  float4 pts[kMsPtTile];
+  float red[kMsWarps];
+  int warp_scan[kMsWarps];
+  int ticket;
+};
+
+__global__ void __launch_bounds__(kMsThreads, 4) ms_iterate_kernel(MsArgs a) {
+  extern __shared__ __align__(16) unsigned char ms_smem_raw[];
+  MsIterSmem &sm = *reinterpret_cast<MsIterSmem *>(ms_smem_raw);
+  cg::grid_group grid = cg::this_grid();
+  const int t = threadIdx.x;
+  const int R = a.cfg[3];
+  const int tile_seeds = kMsThreads * R;
+  const int per_thread = (a.n_fits + kMsThreads - 1) / kMsThreads;  // <= 16
+
+  for (int it = 1;; ++it) {
+    // ---- decisions on iteration it-1, tile prefix of the still-active fits -------------------
+    const int prev = (it + 2) % 3, cur = it % 3, nxt = (it + 1) % 3;
+    int local = 0;
+    const int f_lo = t * per_thread, f_hi = min(a.n_fits, f_lo + per_thread);
+    for (int f = f_lo; f < f_hi; ++f) {
+      int dn = a.done[f];
+      if (!dn && it > 1) {
+        const float m = __uint_as_float(a.fitmax[static_cast<size_t>(prev) * a.n_fits + f]);
+        // reference loop: it += 1; ...; if max(Adis) < stop_thresh or it > max_iter: break
+        bool stop = (m < a.stop_thresh) || (it - 1 > a.max_iter);
+        if (a.flags & PVN3D_MS_EARLY_EXIT)
+          stop = stop || (a.star_shift[static_cast<size_t>((it - 1) & 1) * a.n_fits + f] <= a.eps_stat);
+        if (stop) {
+          dn = 1;
+          a.done[f] = 1;  // every CTA derives the same value from the same data
+          a.iters[f] = it - 1;
+        }
+      }
+      a.fitmax[static_cast<size_t>(nxt) * a.n_fits + f] = 0u;  // consumed two barriers ago
+      const int tiles = dn ? 0 : (a.fit_count[f] + tile_seeds - 1) / tile_seeds;
+      sm.prefix[f] = tiles;  // per-fit tile count, turned into a prefix below
+      local += tiles;
+    }
+    int total;
+    int excl = block_exclusive_scan<kMsThreads>(local, sm.warp_scan, &total);
+    for (int f = f_lo; f < f_hi; ++f) {
+      const int tiles = sm.prefix[f];
+      sm.prefix[f] = excl;
+      excl += tiles;
+    }
+    if (t == 0) sm.prefix[a.n_fits] = total;
+    __syncthreads();
+    if (total == 0) break;  // identical in every CTA
+    if (blockIdx.x == 0 && t == 0) a.cfg[nxt] = 0;  // ticket counter of the next iteration
+
+    // ---- tiles of this iteration, handed out dynamically -------------------------------------
+    for (;;) {
+      if (t == 0) sm.ticket = atomicAdd(a.cfg + cur, 1);
+      __syncthreads();
+      const int tk = sm.ticket;
+      __syncthreads();
+      if (tk >= total) break;
+      const int f = find_segment(sm.prefix, a.n_fits, tk);
+      const int tile_in_fit = tk - sm.prefix[f];
+      if (R == 4) ms_process_tile<4>(a, f, tile_in_fit, cur, it & 1, sm.pts, sm.red);
+      else if (R == 2) ms_process_tile<2>(a, f, tile_in_fit, cur, it & 1, sm.pts, sm.red);
+      else ms_process_tile<1>(a, f, tile_in_fit, cur, it & 1, sm.pts, sm.red);
+    }
+    grid.sync();
+  }
+
+  // ---- results: C[max_idx] back in world coordinates (meanshift_pytorch.py:51) -----------------
+  for (int f = blockIdx.x * kMsThreads + t; f < a.n_fits; f += gridDim.x * kMsThreads) {
+    const int cnt = a.fit_count[f];
+    if (cnt <= 0) continue;
+    const int start = a.fit_start[f], mi = a.max_idx[f];
+    const float4 o = a.pts[start + mi];
+    const float4 c = a.seeds[start + mi];
+    a.ctr[f] = make_float4(c.x + o.x, c.y + o.y, c.z + o.z, static_cast<float>(a.iters[f]));
+  }
+}
+
+// smallest float t2 such that sqrtf(t2) >= bwf  =>  (sqrtf(d2) < bwf) == (d2 < t2) for all d2 >= 0
+float density_threshold(float bwf) {
+  if (!(bwf > 0.f)) return 0.f;  // nothing is < 0
+  float t = bwf * bwf;
+  while (sqrtf(t) >= bwf && t > 0.f) t = nextafterf(t, 0.f);
+  while (sqrtf(t) < bwf) t = nextafterf(t, INFINITY);
+  return t;
+}
+
+struct MsLayout {
+  size_t cpts, seeds, best_key, fitmax, done, iters, star, dens_prefix, cfg, total;
+};
+MsLayout ms_layout(int cap, int n_fits) {
+  MsLayout L;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t at = off;
+    off = align_up(off + bytes, 256);
+    return at;
+  };
+  const size_t nf = n_fits > 0 ? n_fits : 1, cp = cap > 0 ? cap : 1;
+  L.cpts = take(cp * sizeof(float4));
+  L.seeds = take(cp * sizeof(float4));
+  L.best_key = take(nf * sizeof(unsigned long long));
+  L.fitmax = take(3 * nf * sizeof(unsigned));
+  L.done = take(nf * sizeof(int));
+  L.iters = take(nf * sizeof(int));
+  L.star = take(2 * nf * sizeof(float));
+  L.dens_prefix = take((nf + 1) * sizeof(int));
+  L.cfg = take(16 * sizeof(int));
+  L.total = off;
+  return L;
+}
+
+int ms_persistent_grid(int *out) {
+  static int cached[64] = {0};
+  int dev = 0;
+  PVN3D_CUDA_TRY(cudaGetDevice(&dev), "cudaGetDevice");
+  if (dev >= 0 && dev < 64 && cached[dev] > 0) {
+    *out = cached[dev];
+    return PVN3D_OK;
+  }
+  PVN3D_CUDA_TRY(cudaFuncSetAttribute(ms_iterate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)sizeof(MsIterSmem)),
+                 "ms_iterate smem attr");
+  int per_sm = 0, sms = 0;
+  PVN3D_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ms_iterate_kernel,
+                                                               kMsThreads, sizeof(MsIterSmem)),
+                 "ms_iterate occupancy");
+  PVN3D_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "sm count");
+  if (per_sm < 1 || sms < 1) return PVN3D_ERR_UNSUPPORTED;
+  *out = per_sm * sms;
+  if (dev >= 0 && dev < 64) cached[dev] = *out;
+  return PVN3D_OK;
+}
+
+}  // namespace
+
+// internal entry shared with poses.cu: fits already described on device, workspace carved by caller
+int meanshift_launch(const float4 *pts, const int *fit_start, const int *fit_count, int n_fits,
+                     int cap, double bandwidth, int max_iter, unsigned flags, float4 *ctr,
+                     uint8_t *labels, int *max_idx, int *n_in, unsigned char *ws, cudaStream_t st) {
+  if (n_fits <= 0) return PVN3D_OK;
+  int grid = 0;
+  int rc = ms_persistent_grid(&grid);
+  if (rc != PVN3D_OK) return rc;
+  const float bwf = static_cast<float>(bandwidth);
+  const MsLayout L = ms_layout(cap, n_fits);
+  for (int f0 = 0; f0 < n_fits; f0 += kMsFitMax) {
+    const int nf = std::min(kMsFitMax, n_fits - f0);
+    MsArgs a;
+    a.pts = pts;
+    a.fit_start = fit_start + f0;
+    a.fit_count = fit_count + f0;
+    a.n_fits = nf;
+    a.t2 = density_threshold(bwf);
+    a.stop_thresh = static_cast<float>(bandwidth * 1e-3);
+    a.eps_stat = static_cast<float>(bandwidth * 1e-6);
+    a.kexp = static_cast<float>(-1.4426950408889634 / (2.0 * bandwidth * bandwidth));
+    a.max_iter = max_iter;
+    a.flags = flags;
+    a.ctr = ctr + f0;
+    a.labels = labels;
+    a.max_idx = max_idx + f0;
+    a.n_in = n_in + f0;
+    a.cpts = reinterpret_cast<float4 *>(ws + L.cpts);
+    a.seeds = reinterpret_cast<float4 *>(ws + L.seeds);
+    a.best_key = reinterpret_cast<unsigned long long *>(ws + L.best_key) + f0;
+    a.fitmax = reinterpret_cast<unsigned *>(ws + L.fitmax) + 3 * static_cast<size_t>(f0);
+    a.done = reinterpret_cast<int *>(ws + L.done) + f0;
+    a.iters = reinterpret_cast<int *>(ws + L.iters) + f0;
+    a.star_shift = reinterpret_cast<float *>(ws + L.star) + 2 * static_cast<size_t>(f0);
+    a.dens_prefix = reinterpret_cast<int *>(ws + L.dens_prefix);
+    a.cfg = reinterpret_cast<int *>(ws + L.cfg);
+    a.grid_ctas = grid;
+
+    ms_setup_kernel<<<1, 1024, 0, st>>>(a);
+    if ((rc = check_launch("ms_setup_kernel")) != PVN3D_OK) return rc;
+    // upper bound on density tiles: every fit wastes < 1 tile
+    const int tiles = ceil_div(cap, kMsThreads) + nf;
+    ms_density_kernel<<<tiles, kMsThreads, 0, st>>>(a);
+    if ((rc = check_launch("ms_density_kernel")) != PVN3D_OK) return rc;
+    ms_prepare_kernel<<<tiles, kMsThreads, 0, st>>>(a);
+    if ((rc = check_launch("ms_prepare_kernel")) != PVN3D_OK) return rc;
+    void *kargs[] = {&a};
+    PVN3D_CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(ms_iterate_kernel),
+                                               dim3(grid), dim3(kMsThreads), kargs,
+                                               sizeof(MsIterSmem), st),
+                   "ms_iterate_kernel launch");
+  }
+  return PVN3D_OK;
+}
+
+size_t meanshift_ws_bytes(int cap, int n_fits) { return ms_layout(cap, n_fits).total; }
+
+}  // namespace pvn3d
+
+extern "C" size_t pvn3d_meanshift_workspace_bytes(int cap, int n_fits) {
+  return pvn3d::meanshift_ws_bytes(cap, n_fits);
+}
+
+extern "C" int pvn3d_meanshift_fit_batch(const float *pts, const int *fit_start,
+                                         const int *fit_count, int n_fits, int cap,
+                                         double bandwidth, int max_iter, unsigned flags, float *ctr,
+                                         uint8_t *labels, int *max_idx, int *n_in, void *workspace,
+                                         size_t workspace_bytes, pvn3d_stream_t stream) {
+  using namespace pvn3d;
+  if (!pts || !fit_start || !fit_count || !ctr || !max_idx || !n_in || !workspace || n_fits < 0 ||
+      cap < 0 || !(bandwidth > 0.0) || max_iter < 0)
+    return PVN3D_ERR_INVALID_ARG;
+  if (workspace_bytes < meanshift_ws_bytes(cap, n_fits)) return PVN3D_ERR_WORKSPACE;
+  if ((reinterpret_cast<uintptr_t>(pts) & 15u) || (reinterpret_cast<uintptr_t>(ctr) & 15u) ||
+      (reinterpret_cast<uintptr_t>(workspace) & 255u))
+    return PVN3D_ERR_INVALID_ARG;
+  return meanshift_launch(reinterpret_cast<const float4 *>(pts), fit_start, fit_count, n_fits, cap,
+                          bandwidth, max_iter, flags, reinterpret_cast<float4 *>(ctr), labels,
+                          max_idx, n_in, static_cast<unsigned char *>(workspace),
+                          pvn3d::as_stream(stream));
+}
