@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""bench.py -- frames/sec of the per-frame keypoint-voting hot path on synthetic 12288-pt RGB-D clouds.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config linemod|ycb]
+
+Metric / config (BASELINE.json): frames/sec, LineMOD-shape synthetic, 12288 pts, 1 instance, 8 kps,
+batch 32 per GPU (configs[1]); a step = one pass of hot path A (Pointnet2MSG.forward) + hot path B
+(cal_frame_poses_lm) over one batch.  N > 1 (launched by torchrun): every rank owns its own 32 frames
+(weak scaling, frames sharded across ranks, no data-path collective) and the step ends with ONE
+NCCL all_gather of the poses.  Timing: CUDA events around exactly K steps, barrier + synchronize on
+both sides, max over ranks.  Inputs: 4 rotating device-resident batches (252 MB > the 126 MB L2).
+`--impl reference` times the CPU implementation of the same path (oracle port; the reference's
+PointNet++ ops have no CPU path and /root/reference is absent on the GPU box) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_POINTS = 12288
+CONFIGS = {"linemod": dict(batch=32, shape="linemod", config_id=2, label="LineMOD-shape"),
+           "ycb": dict(batch=16, shape="ycb", config_id=3, label="YCB-shape")}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.th = [], None, None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        def pump():
+            for line in self.proc.stdout:
+                self.rows.append(line.strip())
+        self.th = threading.Thread(target=pump, daemon=True)
+        self.th.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        load = [s for s in sm if s > 0]
+        return {"sm_mhz": statistics.median(load) if load else None,
+                "sm_max_mhz": max(smax) if smax else None, "samples": len(load), "reasons": sorted(reasons)}
+
+
+def qg_algorithmic_bytes(b, n, m, c, ns):
+    """fused ball-query+group, one (level, scale): read xyz + new_xyz + feats; write idx + grouped
+    (DESIGN.md section 4)."""
+    return b * (12 * n + 12 * m + 4 * c * n + 4 * m * ns + 4 * (3 + c) * m * ns)
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_sample(frames, sd, iters_per_fit, n_threads, pathb_iters=6):
+    """Time the CPU implementation of the path on a bounded sample of the same workload:
+    hot path A of ONE frame in full, hot path B as `pathb_iters` mean-shift sweeps at the frame's
+    real n_c, scaled to the sweep counts the strict GPU run needed (iters_per_fit: list of T per fit).
+    Returns (seconds per frame, description)."""
+    import torch
+    from oracle import pointnet2_cpu
+    from oracle.meanshift_oracle import MeanShiftOracle, best_fit_transform
+
+    torch.set_num_threads(n_threads)
+    f = frames[0]
+    t0 = time.perf_counter()
+    pointnet2_cpu.forward(f.cld_rgb_nrm[None], sd, threads=n_threads)
+    t_a = time.perf_counter() - t0
+    sel = f.labels == f.cls_ids[0]
+    votes = torch.from_numpy(f.pcld[sel] - f.ctr_of[0][sel])
+    ms = MeanShiftOracle(0.08, max_iter=pathb_iters - 1)       # it > max_iter stops: exactly pathb_iters sweeps
+    t0 = time.perf_counter()
+    ms.fit(votes)
+    t_fit = time.perf_counter() - t0
+    n_sweeps = ms.n_iter + 1                                    # + the density / label pass
+    t_sweep = t_fit / n_sweeps
+    total_sweeps = sum(t + 1 for t in iters_per_fit)
+    t0 = time.perf_counter()
+    best_fit_transform(np.random.rand(9, 3).astype(np.float32), np.random.rand(9, 3).astype(np.float32))
+    t_b = total_sweeps * t_sweep + (time.perf_counter() - t0)
+    desc = (f"1 frame: hot path A in full ({t_a:.2f}s); hot path B = {n_sweeps} torch-CPU mean-shift sweeps at "
+            f"n_c={int(sel.sum())} ({t_sweep * 1e3:.0f} ms/sweep) scaled to the {total_sweeps} sweeps "
+            f"({len(iters_per_fit)} fits) of the frame")
+    return t_a + t_b, desc
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="linemod", choices=list(CONFIGS))
+    ap.add_argument("--early-exit", action="store_true", help="mean-shift early exit (see DESIGN.md section 5)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3 if args.impl == "b200" else 0)
+    cfg = CONFIGS[args.config]
+
+    import torch
+    from pvn3d_b200 import dist as pdist, synth, testing
+
+    rank, local_rank, world = pdist.env_rank_world()
+    n_threads = os.cpu_count() or 1
+    workload = f"{cfg['label']} synthetic, {N_POINTS} pts, 8 kps, batch {cfg['batch']}/GPU, strict mean-shift stop rule"
+
+    # ------------------------------------------------------------------ reference arm (CPU oracle port)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        kw = dict(lm_obj_id=1) if cfg["shape"] == "linemod" else {}
+        frames = synth.make_batch(cfg["shape"], 1, n_points=N_POINTS, config_id=cfg["config_id"], **kw)
+        sd = testing.seeded_pointnet2msg(0, 1).state_dict()
+        # sweep counts of the frame's fits come from the oracle itself on a sub-sampled vote set (cheap)
+        iters = reference_iters_estimate(frames[0])
+        times, desc = [], ""
+        for s in range(args.warmup + args.steps):
+            t, desc = cpu_reference_sample(frames, sd, iters, n_threads)
+            if s >= args.warmup:
+                times.append(t)
+        sec = statistics.median(times)
+        value = 1.0 / sec
+        line = {"metric": "frames/sec", "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+                "config": {"workload": workload, "n_points": N_POINTS, "parallelism": "host cores"},
+                "cpu_baseline": {"value": value, "unit": "frames/s", "cores": n_threads, "kind": "port", "sample": desc},
+                "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    from pvn3d_b200 import _ext, _lib
+    from pvn3d_b200.pipeline import FramePipeline
+
+    rank, local_rank, world = pdist.init_from_env()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    dev = torch.device(f"cuda:{local_rank}")
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+    B = cfg["batch"]
+    lm_obj = 1   # 'ape': one LineMOD object per batch (cal_frame_poses_lm takes a single obj_id)
+    kw = dict(lm_obj_id=lm_obj) if cfg["shape"] == "linemod" else {}
+    frames = synth.make_batch(cfg["shape"], B, n_points=N_POINTS, config_id=cfg["config_id"], first_frame=rank * B, **kw)
+    pipe = FramePipeline(cfg["shape"], B, n_points=N_POINTS, device=dev, lm_obj_id=lm_obj, early_exit=args.early_exit)
+    host = synth.stack(frames)
+    n_rot = 4
+    host_rot = [FramePipeline.pin_batch({k: np.roll(v, 8 * r, axis=0) for k, v in host.items()}) for r in range(n_rot)]
+    dev_rot = [{k: v.to(dev) for k, v in hb.items()} for hb in host_rot]
+    rot_bytes = sum(v.numel() * v.element_size() for v in dev_rot[0].values()) * n_rot
+
+    def step_device(i):
+        d = dev_rot[i % n_rot]
+        poses, present = pipe.run_device(d["cld_rgb_nrm"], d["pcld"], d["labels"], d["ctr_of"], d["kp_of"])
+        if world > 1:   # the single collective of the path: ~1.5 kB per frame
+            torch.distributed.all_gather_into_tensor(gather_buf, poses.reshape(-1))
+        return poses
+
+    def step_host(i):
+        poses, present = pipe.run_host(host_rot[i % n_rot])
+        if world > 1:
+            torch.distributed.all_gather_into_tensor(gather_buf, pipe.solver.poses.reshape(-1))
+        return poses
+
+    gather_buf = torch.empty((world * B * pipe.n_cls * 12,), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.pvn3d_launch_count()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        return pdist.max_over_ranks(ms, dev), lib.pvn3d_launch_count() - l0
+
+    for i in range(args.warmup):
+        step_device(i)
+        step_host(i)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches = timed(step_device, args.steps)
+    ms_e2e, _ = timed(step_host, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    total_frames = B * world * args.steps
+    value = total_frames / (ms_dev * 1e-3)
+    e2e_value = total_frames / (ms_e2e * 1e-3)
+
+    # ---- stage split (device-timed, one extra pass) + mean-shift sweep counts ---------------------------
+    d = dev_rot[0]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    torch.cuda.synchronize(dev)
+    ev[0].record()
+    with torch.no_grad():
+        pipe.model(d["cld_rgb_nrm"])
+    ev[1].record()
+    pipe.solver.solve(d["pcld"], d["labels"], d["ctr_of"], d["kp_of"])
+    ev[2].record()
+    torch.cuda.synchronize(dev)
+    ms_a, ms_b = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
+
+    # ---- roofline of the fused ball-query+group kernel (HBM-bound; BASELINE.json north_star) ------------
+    peak, peak_kind = load_peaks()
+    roof = None
+    if rank == 0:
+        roof = roofline_query_group(torch, _ext, dev, B, d["cld_rgb_nrm"], peak, peak_kind)
+
+    line = None
+    if rank == 0:
+        line = {"metric": "frames/sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload, "n_points": N_POINTS, "global_batch": B * world,
+                           "parallelism": f"frame-sharded x{world}, one NCCL all_gather of poses per step" if world > 1 else "1 GPU",
+                           "l2": f"{n_rot} rotating device-resident input batches ({rot_bytes / 1e6:.0f} MB) > L2",
+                           "mlp": "cuDNN/cuBLAS 1x1 conv (TF32 allowed, as the reference's torch default)",
+                           "meanshift": "early-exit" if args.early_exit else "strict (reference global stop rule)"},
+                "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": pipe.h2d_bytes(),
+                        "d2h_bytes_per_step": pipe.d2h_bytes(), "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+                "stage_ms_per_batch": {"hot_path_A_pointnet2msg": ms_a, "hot_path_B_meanshift_pose": ms_b},
+                "meanshift_ms_per_frame": ms_b / B}
+        if world == 1 and not args.no_cpu_baseline:
+            iters = gpu_iters_per_fit(pipe, d, frame=0)
+            sd = pipe.model.state_dict()
+            sec, desc = cpu_reference_sample(frames, sd, iters, n_threads)
+            line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "frames/s", "cores": n_threads, "kind": "port",
+                                    "sample": desc}
+            line["meanshift_sweeps_frame0"] = iters
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
+def gpu_iters_per_fit(pipe, d, frame=0):
+    """sweep counts (T per fit) the strict GPU run needed for one frame: centre fit + 8 keypoint fits
+    of every present class (read back from the solver's workspace-independent outputs)."""
+    import torch
+    from pvn3d_b200.meanshift import MeanShiftTorch
+
+    labels = d["labels"][frame]
+    pcld, ctr_of, kp_of = d["pcld"][frame], d["ctr_of"][frame], d["kp_of"][frame]
+    iters = []
+    ms = MeanShiftTorch(0.08)
+    for c in torch.unique(labels[labels > 0]).tolist():
+        sel = labels == c
+        ctr, lab = ms.fit(pcld[sel] - ctr_of[sel])
+        iters.append(int(ms.last_iters[0].item()))
+        clouds = [pcld[sel] - kp_of[k][sel] for k in range(kp_of.shape[0])]
+        ms.fit_many(clouds)
+        iters += [int(x) for x in ms.last_iters.tolist()]
+    return iters
+
+
+def reference_iters_estimate(frame):
+    """CPU-only estimate of the sweep counts for the --impl reference leg: run the oracle on a
+    512-point subsample of each vote set (iteration counts are set by the outlier geometry, not by n)."""
+    import torch
+    from oracle.meanshift_oracle import MeanShiftOracle
+
+    rng = np.random.default_rng(0)
+    iters = []
+    for c in frame.cls_ids:
+        sel = np.nonzero(frame.labels == c)[0]
+        sub = np.sort(rng.choice(sel, size=min(512, len(sel)), replace=False))
+        for off in [frame.ctr_of[0]] + [frame.kp_of[k] for k in range(frame.kp_of.shape[0])]:
+            ms = MeanShiftOracle(0.08)
+            ms.fit(torch.from_numpy(frame.pcld[sub] - off[sub]))
+            iters.append(ms.n_iter)
+    return iters
+
+
+def roofline_query_group(torch, _ext, dev, B, cloud, peak, peak_kind):
+    """Launch the fused ball-query+group kernel for the 8 (level, scale) pairs of one batch with real
+    level geometry, time every launch with CUDA events on the launching stream (L2 flushed in between),
+    and report achieved algorithmic HBM bytes/s against the measured copy bandwidth."""
+    from pvn3d_b200.pointnet2 import SA_SPEC
+
+    xyz = cloud[..., :3].contiguous()
+    feat_pm, ldf, c = cloud, 9, 6
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    total_bytes = total_ms = 0.0
+    per = []
+    chans = [6, 96, 256, 512]
+    for li, (npoint, radii, nsamples, _) in enumerate(SA_SPEC):
+        n = xyz.size(1)
+        idx = _ext.furthest_point_sampling(xyz, npoint)
+        new_xyz = torch.gather(xyz, 1, idx.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+        if li == 0:
+            fp, ld, cc = cloud[..., 3:].contiguous(), 6, 6
+        else:
+            cc = chans[li]
+            fp, ld = torch.randn(B, n, cc, device=dev), cc
+        for r, ns in zip(radii, nsamples):
+            ms_l = []
+            for rep in range(3):
+                flush.fill_(float(rep))
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _ext.query_and_group(xyz, new_xyz, fp, r, ns, ldf=ld, c=cc, want_idx=True)
+                e1.record()
+                torch.cuda.synchronize(dev)
+                ms_l.append(e0.elapsed_time(e1))
+            ms_k = statistics.median(ms_l)
+            nbytes = qg_algorithmic_bytes(B, n, npoint, cc, ns)
+            per.append({"level": li + 1, "nsample": ns, "MB": nbytes / 1e6, "us": ms_k * 1e3,
+                        "GBps": nbytes / ms_k / 1e6})
+            total_bytes += nbytes
+            total_ms += ms_k
+        xyz = new_xyz
+    achieved = total_bytes / total_ms / 1e6
+    big = max(per, key=lambda p: p["MB"])
+    return {"kernel": "query_group_kernel (fused ball-query+group, 8 launches of one batch)", "bound": "hbm",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
+            "traffic": None, "algorithmic_MB_per_batch": total_bytes / 1e6, "us_per_batch": total_ms * 1e3,
+            "largest_launch": big, "per_launch": per}
+
+
+if __name__ == "__main__":
+    sys.exit(main())

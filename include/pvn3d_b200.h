@@ -45,6 +45,8 @@ int pvn3d_version(void);                 /* ABI version, currently 1            
 const char *pvn3d_strerror(int code);    /* static string                                    */
 const char *pvn3d_last_cuda_error(void); /* thread-local text of the last PVN3D_ERR_CUDA     */
 int pvn3d_device_sm_count(int *sm_count, int *cc_major, int *cc_minor);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+unsigned long long pvn3d_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * Boundary 1: lib.pointnet2_utils._ext

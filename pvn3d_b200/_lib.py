@@ -24,6 +24,7 @@ _SIGNATURES = {
     "pvn3d_strerror": (c_char_p, [c_int]),
     "pvn3d_last_cuda_error": (c_char_p, []),
     "pvn3d_device_sm_count": (c_int, [_P, _P, _P]),
+    "pvn3d_launch_count": (ctypes.c_ulonglong, []),
     "pvn3d_furthest_point_sampling": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "pvn3d_gather_points": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "pvn3d_gather_points_grad": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),

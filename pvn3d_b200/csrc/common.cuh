@@ -10,7 +10,9 @@ namespace pvn3d {
 
 // ---- host-side error plumbing (never exit(); reference cuda_utils.h:30-39 does) -------------
 void note_cuda_error(cudaError_t e, const char *where);
+void count_launch();  // every kernel launch of the library is tallied (pvn3d_launch_count)
 static inline int check_launch(const char *where) {
+  count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     note_cuda_error(e, where);

@@ -478,6 +478,7 @@ int meanshift_launch(const float4 *pts, const int *fit_start, const int *fit_cou
                                                dim3(grid), dim3(kMsThreads), kargs,
                                                sizeof(MsIterSmem), st),
                    "ms_iterate_kernel launch");
+    count_launch();
   }
   return PVN3D_OK;
 }

@@ -7,6 +7,9 @@
 namespace pvn3d {
 
 static thread_local char g_last_err[256] = "";
+static unsigned long long g_launches = 0ull;
+
+void count_launch() { __atomic_fetch_add(&g_launches, 1ull, __ATOMIC_RELAXED); }
 
 void note_cuda_error(cudaError_t e, const char *where) {
   snprintf(g_last_err, sizeof(g_last_err), "%s: %s (%s)", where, cudaGetErrorString(e),
@@ -38,6 +41,10 @@ int ref_opt_n_threads(int work_size) {
 extern "C" {
 
 int pvn3d_version(void) { return 1; }
+
+unsigned long long pvn3d_launch_count(void) {
+  return __atomic_load_n(&pvn3d::g_launches, __ATOMIC_RELAXED);
+}
 
 const char *pvn3d_strerror(int code) {
   switch (code) {

@@ -1,0 +1,91 @@
+"""FramePipeline -- the per-frame keypoint-voting hot path as one device-resident call.
+
+    pipe = FramePipeline("linemod", batch=32)                     # or "ycb", batch=16
+    poses, present = pipe.run_host(host_batch)                   # pinned host in, host out (e2e)
+    poses, present = pipe.run_device(cld_rgb_nrm, pcld, labels, ctr_of, kp_of)   # resident inputs
+
+One frame = hot path A (Pointnet2MSG.forward on [N,9]) + hot path B (cal_frame_poses* on that
+frame's votes), the unit BASELINE.json's frames/sec counts.  Both run on the
+current CUDA stream with no host synchronisation; the only copies are the ones run_host() makes.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import fixtures
+from .eval_utils import FramePoseSolver
+from .testing import seeded_pointnet2msg
+
+
+class FramePipeline:
+    def __init__(self, shape: str, batch: int, n_points: int = fixtures.N_SAMPLE_POINTS, device="cuda",
+                 lm_obj_id: int = 1, early_exit: bool = False, model: Optional[torch.nn.Module] = None,
+                 allow_tf32: bool = True):
+        self.dev = torch.device(device)
+        self.shape, self.b, self.n, self.k = shape, int(batch), int(n_points), fixtures.N_KEYPOINTS
+        self.model = (model if model is not None else seeded_pointnet2msg(0, 1)).to(self.dev).eval()
+        if shape == "linemod":
+            self.n_cls = 2
+            mesh = fixtures.mesh_kps_table_lm(lm_obj_id)
+            self.solver = FramePoseSolver(self.b, self.n, self.k, 2, mesh, None, False, device=self.dev,
+                                          early_exit=early_exit)
+        elif shape == "ycb":
+            self.n_cls = fixtures.YCB_N_CLASSES
+            self.solver = FramePoseSolver(self.b, self.n, self.k, self.n_cls, fixtures.mesh_kps_table_ycb(),
+                                          fixtures.radius_thresholds_ycb(), True, device=self.dev,
+                                          early_exit=early_exit)
+        else:
+            raise ValueError(shape)
+        self.allow_tf32 = allow_tf32
+        # device staging buffers for run_host()
+        f32 = dict(dtype=torch.float32, device=self.dev)
+        self.d_cloud = torch.empty((self.b, self.n, 9), **f32)
+        self.d_pcld = torch.empty((self.b, self.n, 3), **f32)
+        self.d_labels = torch.empty((self.b, self.n), dtype=torch.int32, device=self.dev)
+        self.d_ctr_of = torch.empty((self.b, self.n, 3), **f32)
+        self.d_kp_of = torch.empty((self.b, self.k, self.n, 3), **f32)
+        self.h_poses = torch.empty((self.b, self.n_cls, 3, 4), dtype=torch.float32).pin_memory()
+        self.h_present = torch.empty((self.b, self.n_cls), dtype=torch.uint8).pin_memory()
+        self.features = None
+
+    def h2d_bytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in
+                   (self.d_cloud, self.d_pcld, self.d_labels, self.d_ctr_of, self.d_kp_of))
+
+    def d2h_bytes(self) -> int:
+        return self.h_poses.numel() * 4 + self.h_present.numel()
+
+    @staticmethod
+    def pin_batch(batch: Dict[str, np.ndarray]) -> Dict[str, torch.Tensor]:
+        return {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in batch.items()}
+
+    @torch.no_grad()
+    def run_device(self, cld_rgb_nrm, pcld, labels, ctr_of, kp_of):
+        """inputs resident in HBM; returns device views (poses [B,n_cls,3,4], present [B,n_cls])."""
+        prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = self.allow_tf32
+        try:
+            self.features = self.model(cld_rgb_nrm)                       # hot path A: [B,128,N]
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+        poses, present, _, _ = self.solver.solve(pcld, labels, ctr_of, kp_of)   # hot path B
+        return poses, present
+
+    @torch.no_grad()
+    def run_host(self, hb: Dict[str, torch.Tensor]):
+        """hb: pinned host tensors (pin_batch).  H2D copies, both hot paths, D2H of the poses; the
+        caller synchronises the stream before reading the returned pinned host tensors."""
+        b = hb["pcld"].shape[0]
+        self.d_cloud[:b].copy_(hb["cld_rgb_nrm"], non_blocking=True)
+        self.d_pcld[:b].copy_(hb["pcld"], non_blocking=True)
+        self.d_labels[:b].copy_(hb["labels"], non_blocking=True)
+        self.d_ctr_of[:b].copy_(hb["ctr_of"], non_blocking=True)
+        self.d_kp_of[:b].copy_(hb["kp_of"], non_blocking=True)
+        poses, present = self.run_device(self.d_cloud[:b], self.d_pcld[:b], self.d_labels[:b],
+                                         self.d_ctr_of[:b], self.d_kp_of[:b])
+        self.h_poses[:b].copy_(poses, non_blocking=True)
+        self.h_present[:b].copy_(present, non_blocking=True)
+        return self.h_poses[:b], self.h_present[:b]

@@ -1,0 +1,91 @@
+"""Parity of the batched mean-shift kernels with the reference's recorded CPU results.
+
+Bar (BASELINE.json north_star): labels / max_idx / inlier counts bit-exact; voted centres within
+1e-4 RELATIVE of the reference's CPU MeanShift (tolerance written here: |dc| <= 1e-4 * |c|).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from pvn3d_b200.meanshift import MeanShiftTorch
+
+pytestmark = pytest.mark.gpu
+CASES = ["tight", "outl10", "outl30", "two", "wide", "bw002", "bw016", "single", "pair_far", "n1200"]
+REL_TOL = 1e-4
+
+
+def _rel_err(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-12))
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("early_exit", [False, True])
+def test_fit_matches_reference_golden(cuda_dev, golden_dir, name, early_exit):
+    z = np.load(os.path.join(golden_dir, "ms_cases.npz"))
+    A = torch.from_numpy(z[f"{name}_A"]).to(cuda_dev)
+    ms = MeanShiftTorch(bandwidth=float(z[f"{name}_bw"]), early_exit=early_exit)
+    ctr, labels = ms.fit(A)
+    assert labels.dtype == torch.bool and labels.shape == (A.size(0),) and ctr.shape == (3,)
+    assert np.array_equal(labels.cpu().numpy(), z[f"{name}_labels"]), "labels must be bit-exact"
+    assert _rel_err(ctr.cpu().numpy(), z[f"{name}_ctr"]) <= REL_TOL
+    iters = int(ms.last_iters[0].item())
+    if not early_exit:
+        # same global stop rule => same iteration count (a borderline max-shift may move it by one)
+        assert abs(iters - int(z[f"{name}_iters"])) <= 1, (iters, int(z[f"{name}_iters"]))
+    else:
+        assert iters <= int(z[f"{name}_iters"]) + 1
+
+
+def test_fit_many_equals_individual_fits(cuda_dev, golden_dir):
+    z = np.load(os.path.join(golden_dir, "ms_cases.npz"))
+    names = ["tight", "outl10", "two", "wide", "single", "pair_far"]
+    clouds = [torch.from_numpy(z[f"{n}_A"]).to(cuda_dev) for n in names]
+    ms = MeanShiftTorch(bandwidth=0.08)
+    ctrs, labels = ms.fit_many(clouds)
+    for i, n in enumerate(names):
+        c1, l1 = ms.fit(clouds[i])
+        assert torch.equal(l1, labels[i])
+        assert torch.equal(c1, ctrs[i]), "a fit must not depend on what else is in the batch"
+        assert np.array_equal(labels[i].cpu().numpy(), z[f"{n}_labels"])
+
+
+def test_labels_are_mutable_boolean_index(cuda_dev):
+    # callers do ctr_labels[0] = 1 and index with it (pvn3d_eval_utils.py:86-92)
+    g = torch.Generator().manual_seed(0)
+    A = (torch.randn(200, 3, generator=g) * 0.01 + torch.tensor([0.1, 0.0, 0.8])).to(cuda_dev)
+    ctr, labels = MeanShiftTorch(0.08).fit(A)
+    labels[0] = 1
+    assert A[labels, :].shape[1] == 3
+
+
+def test_properties_at_full_size(cuda_dev):
+    """size-independent properties at the size the bench uses (n_c ~ 3000):
+    translation equivariance, permutation invariance of the centre, determinism."""
+    rng = np.random.default_rng(1)
+    n = 3072
+    A = (np.array([0.1, -0.05, 0.8]) + rng.normal(0, 0.005, size=(n, 3))).astype(np.float32)
+    out = rng.choice(n, n // 10, replace=False)
+    A[out] = rng.uniform([-0.5, -0.4, 0.6], [0.5, 0.4, 1.2], size=(len(out), 3)).astype(np.float32)
+    At = torch.from_numpy(A).to(cuda_dev)
+    ms = MeanShiftTorch(0.08)
+    c0, l0 = ms.fit(At)
+    c0b, l0b = ms.fit(At)
+    assert torch.equal(c0, c0b) and torch.equal(l0, l0b), "bitwise deterministic run to run"
+    shift = torch.tensor([0.25, 0.125, -0.0625], device=cuda_dev)     # exactly representable
+    c1, l1 = ms.fit(At + shift)
+    assert float((c1 - shift - c0).norm() / c0.norm()) < REL_TOL
+    perm = torch.from_numpy(rng.permutation(n)).to(cuda_dev)
+    c2, l2 = ms.fit(At[perm])
+    assert float((c2 - c0).norm() / c0.norm()) < REL_TOL
+    assert int(l2.sum()) == int(l0.sum())
+    # the centre is a fixed point: it sits inside the dense cluster
+    assert float((c0.cpu() - torch.tensor([0.1, -0.05, 0.8])).norm()) < 0.003
+    ce, le = MeanShiftTorch(0.08, early_exit=True).fit(At)
+    assert torch.equal(le, l0) and float((ce - c0).norm() / c0.norm()) < REL_TOL
+
+
+def test_cpu_tensor_is_rejected():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        MeanShiftTorch(0.08).fit(torch.zeros(4, 3))

@@ -1,0 +1,53 @@
+"""Hot path A end to end (Pointnet2MSG mirror on the sm_100a ops) against features recorded from the
+REFERENCE Pointnet2MSG (tests/golden/pn2msg.npz), and the FramePipeline on synthetic frames."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from pvn3d_b200 import synth, testing
+from pvn3d_b200.pipeline import FramePipeline
+
+pytestmark = pytest.mark.gpu
+
+
+def test_pointnet2msg_matches_reference_features(cuda_dev, golden_dir):
+    z = np.load(os.path.join(golden_dir, "pn2msg.npz"))
+    model = testing.seeded_pointnet2msg(0, 1).to(cuda_dev)
+    x = torch.from_numpy(z["cld_rgb_nrm"])[None].to(cuda_dev)
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        with torch.no_grad():
+            y = model(x)[0]
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    got = y[:, torch.from_numpy(z["cols"]).long().to(cuda_dev)].cpu().numpy()
+    want = z["feats"]
+    # fp32 MLPs on both sides, identical indices: only summation order differs (1e-4 of the feature scale)
+    scale = float(z["feat_abs_mean"])
+    assert np.abs(got - want).max() <= 2e-3 * max(scale, 1.0), np.abs(got - want).max()
+    assert np.abs(got - want).mean() <= 1e-4 * max(scale, 1.0)
+
+
+@pytest.mark.parametrize("shape,batch", [("linemod", 2), ("ycb", 2)])
+def test_frame_pipeline_recovers_synthetic_poses(cuda_dev, shape, batch):
+    n = 4096
+    frames = synth.make_batch(shape, batch, n_points=n, config_id=9)
+    pipe = FramePipeline(shape, batch, n_points=n, device=cuda_dev,
+                         lm_obj_id=frames[0].obj_id if shape == "linemod" else 1)
+    hb = FramePipeline.pin_batch(synth.stack(frames))
+    poses, present = pipe.run_host(hb)
+    torch.cuda.synchronize()
+    assert pipe.features.shape == (batch, 128, n)
+    poses = poses.numpy()
+    for bi, f in enumerate(frames):
+        if shape == "linemod" and f.obj_id != frames[0].obj_id:
+            continue
+        for ci, c in enumerate(f.cls_ids):
+            assert present[bi, int(c)] == 1
+            gt = f.RTs[ci]
+            # votes carry 5 mm noise: the recovered translation must land within a few mm
+            assert np.linalg.norm(poses[bi, int(c)][:, 3] - gt[:, 3]) < 0.01
+            assert np.linalg.norm(poses[bi, int(c)][:, :3] - gt[:, :3]) < 0.2
