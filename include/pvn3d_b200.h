@@ -89,8 +89,8 @@ int pvn3d_three_nn(const float *unknown, const float *known, int b, int n, int m
                    int *idx, pvn3d_stream_t stream);
 
 /* three_interpolate(points[B,C,M], idx[B,N,3], weight[B,N,3]) -> out[B,C,N]
- * (interpolate_gpu.cu:72-111); sum order p1*w1 + p2*w2 + p3*w3 contracted as the reference
- * SASS does (fmul, fma, fma) => bit-exact. */
+ * (interpolate_gpu.cu:72-111); p1*w1 + p2*w2 + p3*w3 contracted as the reference SASS does
+ * (t = p2*w2; t = fma(p1,w1,t); fma(p3,w3,t)) => bit-exact. */
 int pvn3d_three_interpolate(const float *points, const int *idx, const float *weight, int b, int c,
                             int m, int n, float *out, pvn3d_stream_t stream);
 /* three_interpolate_grad(grad_out[B,C,N], idx, weight, M) -> grad_points[B,C,M].

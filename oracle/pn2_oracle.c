@@ -193,8 +193,8 @@ void oracle_three_nn(const float *unknown, const float *known, int b, int n, int
     }
 }
 
-/* interpolate_gpu.cu:72-101; contraction observed in the reference SASS:
- * t = p1*w1 ; t = fma(p2,w2,t) ; out = fma(p3,w3,t) */
+/* interpolate_gpu.cu:72-101; contraction observed in the reference SASS (oracle/_ref build):
+ * t = p2*w2 ; t = fma(p1,w1,t) ; out = fma(p3,w3,t)   (pinned on the GPU against the reference) */
 void oracle_three_interpolate(const float *points, const int *idx, const float *weight, int b,
                               int c, int m, int n, float *out) {
 #pragma omp parallel for collapse(2)
@@ -205,7 +205,7 @@ void oracle_three_interpolate(const float *points, const int *idx, const float *
         const int *ii = idx + ((size_t)bi * n + j) * 3;
         const float *row = points + ((size_t)bi * c + l) * m;
         out[((size_t)bi * c + l) * n + j] =
-            fmaf(row[ii[2]], w[2], fmaf(row[ii[1]], w[1], row[ii[0]] * w[0]));
+            fmaf(row[ii[2]], w[2], fmaf(row[ii[0]], w[0], row[ii[1]] * w[1]));
       }
 }
 

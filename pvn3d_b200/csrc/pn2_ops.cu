@@ -242,7 +242,8 @@ three_nn_kernel(const float *__restrict__ unknown, const float *__restrict__ kno
 
 // ------------------------------------------------------------------------------------------------
 // three_interpolate: out[b,c,j] = sum_t points[b,c,idx[b,j,t]] * w[b,j,t]   (interpolate_gpu.cu:72-101)
-// contraction as in the reference SASS: t = p1*w1; t = fma(p2,w2,t); out = fma(p3,w3,t)
+// contraction as in the reference SASS (oracle/_ref build, interpolate_gpu.o):
+//   t = p2*w2 (FMUL); t = fma(p1,w1,t); out = fma(p3,w3,t)  -- the MIDDLE product is the bare multiply
 // ------------------------------------------------------------------------------------------------
 __global__ void three_interpolate_kernel(const float *__restrict__ points,
                                          const int *__restrict__ idx,
@@ -257,7 +258,7 @@ __global__ void three_interpolate_kernel(const float *__restrict__ points,
   for (int l = blockIdx.y; l < c; l += gridDim.y) {
     const float *row = points + (static_cast<size_t>(b) * c + l) * m;
     const float v = __fmaf_rn(__ldg(row + i3), w3,
-                              __fmaf_rn(__ldg(row + i2), w2, __fmul_rn(__ldg(row + i1), w1)));
+                              __fmaf_rn(__ldg(row + i1), w1, __fmul_rn(__ldg(row + i2), w2)));
     out[(static_cast<size_t>(b) * c + l) * n + j] = v;
   }
 }
@@ -351,7 +352,7 @@ three_nn_interp_kernel(const float *__restrict__ unknown, const float *__restric
     const float *p3 = feat_b + static_cast<size_t>(s_i[lj][2]) * c;
     float *o = out_pm + (static_cast<size_t>(b) * n + j0 + lj) * ldo + col0;
     for (int ch = lane; ch < c; ch += 32)
-      o[ch] = __fmaf_rn(__ldg(p3 + ch), w3, __fmaf_rn(__ldg(p2 + ch), w2, __fmul_rn(__ldg(p1 + ch), w1)));
+      o[ch] = __fmaf_rn(__ldg(p3 + ch), w3, __fmaf_rn(__ldg(p1 + ch), w1, __fmul_rn(__ldg(p2 + ch), w2)));
   }
 }
 
