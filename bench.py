@@ -242,6 +242,20 @@ def main():
     total_frames = B * world * args.steps
     value = total_frames / (ms_dev * 1e-3)
     e2e_value = total_frames / (ms_e2e * 1e-3)
+    # opt-in mode for comparison: mean-shift stops as soon as the returned seed is stationary
+    early = None
+    if not args.early_exit:
+        from pvn3d_b200.eval_utils import FramePoseSolver
+        strict_solver = pipe.solver
+        pipe.solver = FramePoseSolver(B, N_POINTS, pipe.k, pipe.n_cls, strict_solver.mesh_kps.cpu().numpy(),
+                                      None if strict_solver.cls_radius is None else strict_solver.cls_radius.cpu().numpy(),
+                                      strict_solver.use_filter, device=dev, early_exit=True)
+        for i in range(2):
+            step_device(i)
+        ms_early, _ = timed(step_device, args.steps)
+        early = {"value": total_frames / (ms_early * 1e-3), "unit": "frames/s", "ms_per_step": ms_early / args.steps,
+                 "note": "PVN3D_MS_EARLY_EXIT: same centres to ~1e-7 m, iteration count not the reference's"}
+        pipe.solver = strict_solver
 
     # ---- stage split (device-timed, one extra pass) + mean-shift sweep counts ---------------------------
     d = dev_rot[0]
@@ -276,7 +290,7 @@ def main():
                         "d2h_bytes_per_step": pipe.d2h_bytes(), "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
                 "stage_ms_per_batch": {"hot_path_A_pointnet2msg": ms_a, "hot_path_B_meanshift_pose": ms_b},
-                "meanshift_ms_per_frame": ms_b / B}
+                "meanshift_ms_per_frame": ms_b / B, "meanshift_early_exit": early}
         if world == 1 and not args.no_cpu_baseline:
             iters = gpu_iters_per_fit(pipe, d, frame=0)
             sd = pipe.model.state_dict()

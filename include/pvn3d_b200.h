@@ -134,8 +134,9 @@ int pvn3d_three_nn_interpolate(const float *unknown, const float *known, const f
  * ---------------------------------------------------------------------------------------- */
 
 /* Flags for the mean-shift iteration */
-#define PVN3D_MS_STRICT 0u      /* iterate every seed until the reference's global stop rule   */
-#define PVN3D_MS_EARLY_EXIT 1u  /* additionally stop a fit once the RETURNED seed is stationary */
+#define PVN3D_MS_STRICT 0u      /* the reference's global stop rule decides the iteration count T */
+#define PVN3D_MS_EARLY_EXIT 1u  /* additionally stop a fit once the RETURNED seed is stationary    */
+#define PVN3D_MS_NO_FREEZE 2u   /* validation: keep sweeping seeds that have stopped moving        */
 
 /* A batch of F independent MeanShiftTorch(bandwidth, max_iter).fit(A_f) problems.
  *   pts        [cap,4] f32  vote clouds (x,y,z,unused); fit f owns rows
@@ -151,10 +152,11 @@ int pvn3d_three_nn_interpolate(const float *unknown, const float *known, const f
  *   labels   [cap]   u8   1 where |A[max_idx]-A_j| < bandwidth, indexed like pts (NULL to skip)
  *   max_idx  [F]    i32   first index (within the fit) of the densest input point
  *   n_in     [F]    i32   its inlier count
- * workspace: pvn3d_meanshift_workspace_bytes(cap, n_fits) bytes, 256-B aligned.
+ * workspace: pvn3d_meanshift_workspace_bytes(cap, n_fits, max_iter) bytes, 256-B aligned
+ *            (max_iter <= 4094).
  * Semantics follow meanshift_pytorch.py:24-51 (stop when max_i |dC_i| < bandwidth*1e-3 or
  * it > max_iter; densest *input* point selects the returned seed; first-index arg-max). */
-size_t pvn3d_meanshift_workspace_bytes(int cap, int n_fits);
+size_t pvn3d_meanshift_workspace_bytes(int cap, int n_fits, int max_iter);
 int pvn3d_meanshift_fit_batch(const float *pts, const int *fit_start, const int *fit_count,
                               int n_fits, int cap, double bandwidth, int max_iter, unsigned flags,
                               float *ctr, uint8_t *labels, int *max_idx, int *n_in,
@@ -180,7 +182,7 @@ int pvn3d_best_fit_transform_batch(const float *a, const float *b, const uint8_t
  *   cls_kps  [B,n_cls,K+1,3] f32 voted keypoints + centre (NULL to skip)
  *   new_mask [B,N] i32           relabelled mask of the filter pass (NULL to skip)        (:66-72)
  * use_ctr must be 1 (the reference's use_ctr=False branch is never exercised: SURVEY App. A.5). */
-size_t pvn3d_frame_poses_workspace_bytes(int b, int n, int k, int n_cls);
+size_t pvn3d_frame_poses_workspace_bytes(int b, int n, int k, int n_cls, int max_iter);
 int pvn3d_frame_poses_batch(const float *pcld, const int *mask, const float *ctr_of,
                             const float *kp_of, int b, int n, int k, int n_cls,
                             const float *mesh_kps, const float *cls_radius, int use_ctr_clus_flter,

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libpvn3d_b200.so")
 
 PVN3D_MS_STRICT = 0
 PVN3D_MS_EARLY_EXIT = 1
+PVN3D_MS_NO_FREEZE = 2
 
 _ERR_NAMES = {-1: "invalid argument", -2: "unsupported size", -3: "CUDA error", -4: "workspace too small"}
 
@@ -38,10 +39,10 @@ _SIGNATURES = {
     "pvn3d_transpose_nc_to_cn": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "pvn3d_query_and_group": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_float, c_int, _P, _P, _P]),
     "pvn3d_three_nn_interpolate": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, _P, _P]),
-    "pvn3d_meanshift_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "pvn3d_meanshift_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pvn3d_meanshift_fit_batch": (c_int, [_P, _P, _P, c_int, c_int, c_double, c_int, c_uint, _P, _P, _P, _P, _P, c_size_t, _P]),
     "pvn3d_best_fit_transform_batch": (c_int, [_P, _P, _P, c_int, c_int, _P, _P]),
-    "pvn3d_frame_poses_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "pvn3d_frame_poses_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "pvn3d_frame_poses_batch": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_double, c_int, c_uint, _P, _P, _P, _P, _P, c_size_t, _P]),
 }
 # optional entry points (later build stages); bound when present

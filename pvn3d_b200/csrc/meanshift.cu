@@ -36,8 +36,9 @@ namespace pvn3d {
 namespace {
 
 constexpr int kMsThreads = 256;
-constexpr int kMsFitMax = 4096;  // fits per launch chunk (prefix array lives in shared memory)
-constexpr int kMsPtTile = 1024;  // points per shared-memory tile (16 KB)
+constexpr int kMsFitMax = 2048;  // fits per launch chunk (prefix array lives in shared memory)
+constexpr int kMsPtTile = 4096;  // points per shared-memory tile of the sweep (64 KB)
+constexpr int kMsDensTile = 1024;  // points per tile of the density pass (16 KB static)
 constexpr int kMsWarps = kMsThreads / 32;
 
 struct MsArgs {
@@ -60,13 +61,18 @@ struct MsArgs {
   float4 *cpts;
   float4 *seeds;
   unsigned long long *best_key;
-  unsigned *fitmax;  // [3][n_fits]
   int *done;
-  int *iters;
-  float *star_shift;  // [2][n_fits] shift of the returned seed, double-buffered by iteration parity
+  int *iters;        // T per fit
+  int *star_it;      // first iteration at which the returned seed was stationary (0 = not yet)
+  int *act;          // [3][cap]   work lists: indices (within the fit) of the seeds still moving
+  int *act_cnt;      // [3][n_fits]
+  unsigned *viol;    // [n_fits][viol_words] bit `it` = some seed moved >= stop_thresh at iteration it
+  float4 *traj;      // [n_fits][traj_stride] positions of the returned seed per iteration
   int *dens_prefix;  // [n_fits+1]
-  int *cfg;          // [0..2] tickets, [3] R (seeds per thread), [4] total points
-  int grid_ctas;     // CTAs of the persistent kernel (for the R heuristic)
+  int *cfg;          // [0..2] ticket counters of the phases
+  int cap;
+  int viol_words;
+  int traj_stride;
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -117,17 +123,17 @@ __global__ void __launch_bounds__(1024) ms_setup_kernel(MsArgs a) {
   const int t = threadIdx.x;
   if (t == 0) s_run = 0;
   __syncthreads();
-  long long pts_total = 0;
   for (int f0 = 0; f0 < a.n_fits; f0 += 1024) {
     const int f = f0 + t;
     int cnt = 0;
     if (f < a.n_fits) {
       cnt = max(a.fit_count[f], 0);
       a.best_key[f] = 0ull;
-      a.fitmax[f] = a.fitmax[a.n_fits + f] = a.fitmax[2 * a.n_fits + f] = 0u;
       a.done[f] = cnt == 0;
       a.iters[f] = 0;
-      a.star_shift[f] = a.star_shift[a.n_fits + f] = __int_as_float(0x7f800000);
+      a.star_it[f] = 0;
+      a.act_cnt[f] = a.act_cnt[a.n_fits + f] = a.act_cnt[2 * a.n_fits + f] = 0;
+      for (int w = 0; w < a.viol_words; ++w) a.viol[static_cast<size_t>(f) * a.viol_words + w] = 0u;
       if (cnt == 0) {
         a.ctr[f] = make_float4(0.f, 0.f, 0.f, 0.f);
         a.max_idx[f] = 0;
@@ -138,9 +144,6 @@ __global__ void __launch_bounds__(1024) ms_setup_kernel(MsArgs a) {
     const int excl = block_exclusive_scan<1024>((cnt + kMsThreads - 1) / kMsThreads, s_warp, &total);
     const int run = s_run;
     if (f < a.n_fits) a.dens_prefix[f] = run + excl;
-    int ptot;
-    (void)block_exclusive_scan<1024>(cnt, s_warp, &ptot);
-    pts_total += ptot;
     __syncthreads();
     if (t == 0) s_run = run + total;
     __syncthreads();
@@ -148,19 +151,13 @@ __global__ void __launch_bounds__(1024) ms_setup_kernel(MsArgs a) {
   if (t == 0) {
     a.dens_prefix[a.n_fits] = s_run;
     a.cfg[0] = a.cfg[1] = a.cfg[2] = 0;
-    // seeds per thread: the largest R that still leaves >= 3 tiles per CTA of the persistent grid
-    const long long want = 3ll * a.grid_ctas;
-    int r = 4;
-    while (r > 1 && pts_total / (kMsThreads * r) < want) r >>= 1;
-    a.cfg[3] = r;
-    a.cfg[4] = static_cast<int>(pts_total > 0x7fffffffll ? 0x7fffffffll : pts_total);
   }
 }
 
 // ------------------------------------------------------------------------------------------------
 // exact density pass: one thread per input point, all points of the fit swept from shared memory
 __global__ void __launch_bounds__(kMsThreads) ms_density_kernel(MsArgs a) {
-  __shared__ float4 s_pts[kMsPtTile];
+  __shared__ float4 s_pts[kMsDensTile];
   __shared__ unsigned long long s_key[kMsWarps];
   const int tile = blockIdx.x;
   if (tile >= a.dens_prefix[a.n_fits]) return;
@@ -171,8 +168,8 @@ __global__ void __launch_bounds__(kMsThreads) ms_density_kernel(MsArgs a) {
   const float4 me = a.pts[start + (live ? i : 0)];
   const float t2 = a.t2;
   int count = 0;
-  for (int base = 0; base < cnt; base += kMsPtTile) {
-    const int n = min(kMsPtTile, cnt - base);
+  for (int base = 0; base < cnt; base += kMsDensTile) {
+    const int n = min(kMsDensTile, cnt - base);
     __syncthreads();
     for (int q = threadIdx.x; q < n; q += kMsThreads) s_pts[q] = a.pts[start + base + q];
     __syncthreads();
@@ -212,8 +209,10 @@ __global__ void __launch_bounds__(kMsThreads) ms_prepare_kernel(MsArgs a) {
   if (i == 0) {
     a.max_idx[f] = mi;
     a.n_in[f] = static_cast<int>(key >> 32);
+    a.act_cnt[f] = cnt;  // phase 0 works on every seed
   }
   if (i >= cnt) return;
+  a.act[start + i] = i;
   const float4 o = a.pts[start + mi];
   const float4 p = a.pts[start + i];
   const float dx = p.x - o.x, dy = p.y - o.y, dz = p.z - o.z;
@@ -223,126 +222,224 @@ __global__ void __launch_bounds__(kMsThreads) ms_prepare_kernel(MsArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// one tile of seeds (256*R) of fit f sweeps all of the fit's centred points; returns through
-// atomicMax the tile's largest shift for iteration slot `slot`
-template <int R>
-__device__ __forceinline__ void ms_process_tile(const MsArgs &a, int f, int tile_in_fit, int slot,
-                                                int parity, float4 *s_pts, float *s_red) {
-  const int start = a.fit_start[f], cnt = a.fit_count[f];
-  const int t = threadIdx.x;
-  const float k = a.kexp;
-  float qx[R], qy[R], qz[R], qw[R];
-  float sw[R], sx[R], sy[R], sz[R];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int i = tile_in_fit * (kMsThreads * R) + r * kMsThreads + t;
-    const float4 c = a.seeds[start + (i < cnt ? i : 0)];
-    qx[r] = -2.f * k * c.x;
-    qy[r] = -2.f * k * c.y;
-    qz[r] = -2.f * k * c.z;
-    qw[r] = k * (c.x * c.x + c.y * c.y + c.z * c.z);
-    sw[r] = sx[r] = sy[r] = sz[r] = 0.f;
-  }
-  for (int base = 0; base < cnt; base += kMsPtTile) {
-    const int n = min(kMsPtTile, cnt - base);
-    __syncthreads();
-    for (int q = t; q < n; q += kMsThreads) s_pts[q] = a.cpts[start + base + q];
-    __syncthreads();
-#pragma unroll 4
-    for (int j = 0; j < n; ++j) {
-      const float4 p = s_pts[j];  // broadcast
-#pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const float e = fmaf(p.x, qx[r], fmaf(p.y, qy[r], fmaf(p.z, qz[r], p.w + qw[r])));
-        const float w = ex2_approx(e);
-        sw[r] += w;
-        sx[r] = fmaf(w, p.x, sx[r]);
-        sy[r] = fmaf(w, p.y, sy[r]);
-        sz[r] = fmaf(w, p.z, sz[r]);
-      }
-    }
-  }
-  float mshift = 0.f;
-  const int star = a.max_idx[f];
-#pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const int i = tile_in_fit * (kMsThreads * R) + r * kMsThreads + t;
-    if (i < cnt) {
-      // new_C = sum(w*A)/sum(w); Adis = |new_C - C|   (meanshift_pytorch.py:37-38)
-      const float nx = __fdiv_rn(sx[r], sw[r]), ny = __fdiv_rn(sy[r], sw[r]),
-                  nz = __fdiv_rn(sz[r], sw[r]);
-      const float4 c = a.seeds[start + i];  // old C (re-read: keeps the sweep's register set small)
-      const float sh = __fsqrt_rn(torch_sqnorm(nx - c.x, ny - c.y, nz - c.z));
-      a.seeds[start + i] = make_float4(nx, ny, nz, sh);
-      mshift = fmaxf(mshift, sh);
-      if (i == star) a.star_shift[static_cast<size_t>(parity) * a.n_fits + f] = sh;
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) mshift = fmaxf(mshift, __shfl_xor_sync(0xffffffffu, mshift, o));
-  if ((t & 31) == 0) s_red[t >> 5] = mshift;
-  __syncthreads();
-  if (t == 0) {
-#pragma unroll
-    for (int w = 1; w < kMsWarps; ++w) mshift = fmaxf(mshift, s_red[w]);
-    atomicMax(a.fitmax + static_cast<size_t>(slot) * a.n_fits + f, __float_as_uint(mshift));
-  }
-}
-
+// The iterations.
+//
+// Every seed's trajectory depends only on its own position and the (fixed) points, so seeds need
+// not advance in lock step.  The reference's GLOBAL stop rule -- stop at the first iteration T whose
+// largest shift over ALL seeds is below bw*1e-3 -- is recovered from a per-fit bitmask:
+//   viol[f] bit `it` is set by any seed whose shift at iteration `it` is >= the threshold;
+//   T = the first iteration whose bit is clear (or max_iter+1).
+// A seed whose shift drops below eps = bw*1e-6 (1000x under the threshold) is FROZEN: it can no
+// longer set a bit (its shift cannot grow 1000x again without moving ~9 cm) and
+// moves by < 1e-7 m from then on, so it is dropped from the work list.  The returned seed ("star",
+// the densest input point) logs its position at every iteration, so C[max_idx] AFTER EXACTLY T
+// iterations is what comes back, as in the reference.
+//
+// Work is organised in PHASES of several iterations (6,10,16,32,64,64,...): a tile of seeds keeps
+// its seeds in registers and -- when the fit has <= 4096 points -- the whole point set in shared
+// memory for the entire phase; between phases the still-moving seeds are compacted into dense
+// tiles and a grid barrier lets every CTA take the same per-fit decisions.  Typical vote sets
+// (tight cluster + 10 % outliers) need ~140 iterations by the reference's rule, but after the
+// first phase only the few creeping outlier seeds are still in the lists.
+// ------------------------------------------------------------------------------------------------
 struct MsIterSmem {
-  int prefix[kMsFitMax + 1];
   float4 pts[kMsPtTile];
-  float red[kMsWarps];
+  int prefix[kMsFitMax + 1];
   int warp_scan[kMsWarps];
   int ticket;
 };
 
-__global__ void __launch_bounds__(kMsThreads, 4) ms_iterate_kernel(MsArgs a) {
+__device__ __forceinline__ int ms_phase_end(int p) {  // last iteration of phase p
+  // 6, 16, 32, 64, 128, 192, 256, ...
+  return p == 0 ? 6 : p == 1 ? 16 : p == 2 ? 32 : 64 * (p - 2);
+}
+
+template <int R>
+__device__ __forceinline__ void ms_sweep(const float4 *__restrict__ s_pts, int n, const float (&qx)[R],
+                                         const float (&qy)[R], const float (&qz)[R],
+                                         const float (&qw)[R], float (&sw)[R], float (&sx)[R],
+                                         float (&sy)[R], float (&sz)[R]) {
+#pragma unroll 4
+  for (int j = 0; j < n; ++j) {
+    const float4 p = s_pts[j];  // broadcast LDS.128
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float e = fmaf(p.x, qx[r], fmaf(p.y, qy[r], fmaf(p.z, qz[r], p.w + qw[r])));
+      const float w = ex2_approx(e);
+      sw[r] += w;
+      sx[r] = fmaf(w, p.x, sx[r]);
+      sy[r] = fmaf(w, p.y, sy[r]);
+      sz[r] = fmaf(w, p.z, sz[r]);
+    }
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void ms_run_tile(const MsArgs &a, MsIterSmem &sm, int f, int tile,
+                                            int it_lo, int it_hi, int cur, int nxt) {
+  const int start = a.fit_start[f], n_c = a.fit_count[f];
+  const int n_act = a.act_cnt[static_cast<size_t>(cur) * a.n_fits + f];
+  const int *act_cur = a.act + static_cast<size_t>(cur) * a.cap + start;
+  int *act_nxt = a.act + static_cast<size_t>(nxt) * a.cap + start;
+  const int t = threadIdx.x;
+  const unsigned lane = t & 31u;
+  const float k = a.kexp;
+  const bool single = n_c <= kMsPtTile;  // whole point set stays in shared memory for the phase
+  const bool freeze_on = !(a.flags & PVN3D_MS_NO_FREEZE);
+  const int star = a.max_idx[f];
+
+  int idx[R];
+  float cx[R], cy[R], cz[R], last[R];
+  bool frozen[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const int pos = tile * (kMsThreads * R) + r * kMsThreads + t;
+    const bool valid = pos < n_act;
+    idx[r] = valid ? act_cur[pos] : -1;
+    const float4 c = a.seeds[start + (valid ? idx[r] : 0)];
+    cx[r] = c.x; cy[r] = c.y; cz[r] = c.z; last[r] = c.w;
+    frozen[r] = !valid;
+  }
+  __syncthreads();  // previous tile's readers are done with sm.pts
+  if (single) {
+    for (int q = t; q < n_c; q += kMsThreads) sm.pts[q] = a.cpts[start + q];
+    __syncthreads();
+  }
+
+  for (int it = it_lo; it <= it_hi; ++it) {
+    bool live = false;
+#pragma unroll
+    for (int r = 0; r < R; ++r) live |= !frozen[r];
+    const bool warp_live = __any_sync(0xffffffffu, live);
+    if (single && !warp_live) break;  // no barriers inside the loop in single-tile mode
+
+    float qx[R], qy[R], qz[R], qw[R], sw[R], sx[R], sy[R], sz[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      qx[r] = -2.f * k * cx[r];
+      qy[r] = -2.f * k * cy[r];
+      qz[r] = -2.f * k * cz[r];
+      qw[r] = k * (cx[r] * cx[r] + cy[r] * cy[r] + cz[r] * cz[r]);
+      sw[r] = sx[r] = sy[r] = sz[r] = 0.f;
+    }
+    if (single) {
+      ms_sweep<R>(sm.pts, n_c, qx, qy, qz, qw, sw, sx, sy, sz);
+    } else {
+      for (int base = 0; base < n_c; base += kMsPtTile) {
+        const int n = min(kMsPtTile, n_c - base);
+        __syncthreads();
+        for (int q = t; q < n; q += kMsThreads) sm.pts[q] = a.cpts[start + base + q];
+        __syncthreads();
+        if (warp_live) ms_sweep<R>(sm.pts, n, qx, qy, qz, qw, sw, sx, sy, sz);
+      }
+    }
+    bool violates = false;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (!frozen[r]) {
+        // new_C = sum(w*A)/sum(w); Adis = |new_C - C|   (meanshift_pytorch.py:37-39)
+        const float nx = __fdiv_rn(sx[r], sw[r]), ny = __fdiv_rn(sy[r], sw[r]),
+                    nz = __fdiv_rn(sz[r], sw[r]);
+        const float sh = __fsqrt_rn(torch_sqnorm(nx - cx[r], ny - cy[r], nz - cz[r]));
+        cx[r] = nx; cy[r] = ny; cz[r] = nz; last[r] = sh;
+        violates |= !(sh < a.stop_thresh);
+        const bool still = sh < a.eps_stat;
+        if (idx[r] == star) {
+          a.traj[static_cast<size_t>(f) * a.traj_stride + it] = make_float4(nx, ny, nz, sh);
+          if (still && a.star_it[f] == 0) a.star_it[f] = it;  // only this thread ever writes it
+        }
+        if (still && freeze_on) frozen[r] = true;
+      }
+    }
+    if (__any_sync(0xffffffffu, violates) && lane == 0)
+      atomicOr(a.viol + static_cast<size_t>(f) * a.viol_words + (it >> 5), 1u << (it & 31));
+    if (!single) {
+      bool live2 = false;
+#pragma unroll
+      for (int r = 0; r < R; ++r) live2 |= !frozen[r];
+      if (!__syncthreads_or(live2 ? 1 : 0)) break;
+    }
+  }
+
+  // write the seeds back; the ones still moving go to the next phase's list
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const bool valid = idx[r] >= 0;
+    if (valid) a.seeds[start + idx[r]] = make_float4(cx[r], cy[r], cz[r], last[r]);
+    const bool keep = valid && !frozen[r];
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (m) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(a.act_cnt + static_cast<size_t>(nxt) * a.n_fits + f, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (keep) act_nxt[base + __popc(m & lanemask_lt())] = idx[r];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kMsThreads, 3) ms_iterate_kernel(MsArgs a) {
   extern __shared__ __align__(16) unsigned char ms_smem_raw[];
   MsIterSmem &sm = *reinterpret_cast<MsIterSmem *>(ms_smem_raw);
   cg::grid_group grid = cg::this_grid();
   const int t = threadIdx.x;
-  const int R = a.cfg[3];
-  const int tile_seeds = kMsThreads * R;
-  const int per_thread = (a.n_fits + kMsThreads - 1) / kMsThreads;  // <= 16
+  const int per_thread = (a.n_fits + kMsThreads - 1) / kMsThreads;  // <= 8
+  const int f_lo = min(a.n_fits, t * per_thread), f_hi = min(a.n_fits, f_lo + per_thread);
+  const int last_it = a.max_iter + 1;  // the reference breaks when it > max_iter (:42)
+  const bool early = a.flags & PVN3D_MS_EARLY_EXIT;
 
-  for (int it = 1;; ++it) {
-    // ---- decisions on iteration it-1, tile prefix of the still-active fits -------------------
-    const int prev = (it + 2) % 3, cur = it % 3, nxt = (it + 1) % 3;
-    int local = 0;
-    const int f_lo = t * per_thread, f_hi = min(a.n_fits, f_lo + per_thread);
+  for (int p = 0;; ++p) {
+    const int cur = p % 3, nxt = (p + 1) % 3, nxt2 = (p + 2) % 3;
+    const int prev_lo = p > 0 ? (p > 1 ? ms_phase_end(p - 2) + 1 : 1) : 0;
+    const int prev_hi = p > 0 ? min(ms_phase_end(p - 1), last_it) : 0;
+    const int it_lo = prev_hi + 1, it_hi = min(ms_phase_end(p), last_it);
+
+    // ---- per-fit decisions on the finished phase (identical in every CTA) ---------------------
+    int local_seeds = 0;
     for (int f = f_lo; f < f_hi; ++f) {
       int dn = a.done[f];
-      if (!dn && it > 1) {
-        const float m = __uint_as_float(a.fitmax[static_cast<size_t>(prev) * a.n_fits + f]);
-        // reference loop: it += 1; ...; if max(Adis) < stop_thresh or it > max_iter: break
-        bool stop = (m < a.stop_thresh) || (it - 1 > a.max_iter);
-        if (a.flags & PVN3D_MS_EARLY_EXIT)
-          stop = stop || (a.star_shift[static_cast<size_t>((it - 1) & 1) * a.n_fits + f] <= a.eps_stat);
-        if (stop) {
+      const int n_act = a.act_cnt[static_cast<size_t>(cur) * a.n_fits + f];
+      if (!dn && p > 0) {
+        int tz = 0;
+        const unsigned *vw = a.viol + static_cast<size_t>(f) * a.viol_words;
+        for (int it = prev_lo; it <= prev_hi; ++it)
+          if (!((vw[it >> 5] >> (it & 31)) & 1u)) { tz = it; break; }
+        const int s = a.star_it[f];
+        int T = 0;
+        if (tz) T = (early && s > 0 && s < tz) ? s : tz;
+        else if (early && s > 0) T = s;
+        else if (prev_hi >= last_it) T = last_it;
+        else if (n_act == 0) T = prev_hi;  // cannot happen (an all-frozen fit clears a bit); safe exit
+        if (T) {
           dn = 1;
           a.done[f] = 1;  // every CTA derives the same value from the same data
-          a.iters[f] = it - 1;
+          a.iters[f] = T;
         }
       }
-      a.fitmax[static_cast<size_t>(nxt) * a.n_fits + f] = 0u;  // consumed two barriers ago
-      const int tiles = dn ? 0 : (a.fit_count[f] + tile_seeds - 1) / tile_seeds;
-      sm.prefix[f] = tiles;  // per-fit tile count, turned into a prefix below
-      local += tiles;
+      a.act_cnt[static_cast<size_t>(nxt2) * a.n_fits + f] = 0;  // list of phase p+2, idle since p-1
+      sm.prefix[f] = dn ? 0 : n_act;
+      local_seeds += dn ? 0 : n_act;
     }
+    int total_seeds;
+    (void)block_exclusive_scan<kMsThreads>(local_seeds, sm.warp_scan, &total_seeds);
+    if (total_seeds == 0 || it_lo > last_it) break;  // identical in every CTA
+    // seeds per thread: keep >= 2 tiles per CTA of the grid when there is enough work
+    int R = 2;
+    if (total_seeds / (kMsThreads * R) < 2 * static_cast<int>(gridDim.x)) R = 1;
+    const int tile_seeds = kMsThreads * R;
+    int local_tiles = 0;
+    for (int f = f_lo; f < f_hi; ++f) local_tiles += (sm.prefix[f] + tile_seeds - 1) / tile_seeds;
     int total;
-    int excl = block_exclusive_scan<kMsThreads>(local, sm.warp_scan, &total);
+    int excl = block_exclusive_scan<kMsThreads>(local_tiles, sm.warp_scan, &total);
     for (int f = f_lo; f < f_hi; ++f) {
-      const int tiles = sm.prefix[f];
+      const int tiles = (sm.prefix[f] + tile_seeds - 1) / tile_seeds;
       sm.prefix[f] = excl;
       excl += tiles;
     }
     if (t == 0) sm.prefix[a.n_fits] = total;
     __syncthreads();
-    if (total == 0) break;  // identical in every CTA
-    if (blockIdx.x == 0 && t == 0) a.cfg[nxt] = 0;  // ticket counter of the next iteration
+    if (blockIdx.x == 0 && t == 0) a.cfg[nxt] = 0;  // ticket counter of the next phase
 
-    // ---- tiles of this iteration, handed out dynamically -------------------------------------
+    // ---- tiles of this phase, handed out dynamically -------------------------------------------
     for (;;) {
       if (t == 0) sm.ticket = atomicAdd(a.cfg + cur, 1);
       __syncthreads();
@@ -350,22 +447,24 @@ __global__ void __launch_bounds__(kMsThreads, 4) ms_iterate_kernel(MsArgs a) {
       __syncthreads();
       if (tk >= total) break;
       const int f = find_segment(sm.prefix, a.n_fits, tk);
-      const int tile_in_fit = tk - sm.prefix[f];
-      if (R == 4) ms_process_tile<4>(a, f, tile_in_fit, cur, it & 1, sm.pts, sm.red);
-      else if (R == 2) ms_process_tile<2>(a, f, tile_in_fit, cur, it & 1, sm.pts, sm.red);
-      else ms_process_tile<1>(a, f, tile_in_fit, cur, it & 1, sm.pts, sm.red);
+      const int tile = tk - sm.prefix[f];
+      if (R == 2) ms_run_tile<2>(a, sm, f, tile, it_lo, it_hi, cur, nxt);
+      else ms_run_tile<1>(a, sm, f, tile, it_lo, it_hi, cur, nxt);
     }
     grid.sync();
   }
 
-  // ---- results: C[max_idx] back in world coordinates (meanshift_pytorch.py:51) -----------------
+  // ---- results: C[max_idx] after exactly T iterations, back in world coordinates (:51) -----------
   for (int f = blockIdx.x * kMsThreads + t; f < a.n_fits; f += gridDim.x * kMsThreads) {
     const int cnt = a.fit_count[f];
     if (cnt <= 0) continue;
     const int start = a.fit_start[f], mi = a.max_idx[f];
+    const int T = a.iters[f], s = a.star_it[f];
+    const bool frozen_before_T = !(a.flags & PVN3D_MS_NO_FREEZE) && s > 0 && T >= s;
+    const float4 c = frozen_before_T ? a.seeds[start + mi]
+                                     : a.traj[static_cast<size_t>(f) * a.traj_stride + T];
     const float4 o = a.pts[start + mi];
-    const float4 c = a.seeds[start + mi];
-    a.ctr[f] = make_float4(c.x + o.x, c.y + o.y, c.z + o.z, static_cast<float>(a.iters[f]));
+    a.ctr[f] = make_float4(c.x + o.x, c.y + o.y, c.z + o.z, static_cast<float>(T));
   }
 }
 
@@ -379,9 +478,10 @@ float density_threshold(float bwf) {
 }
 
 struct MsLayout {
-  size_t cpts, seeds, best_key, fitmax, done, iters, star, dens_prefix, cfg, total;
+  size_t cpts, seeds, best_key, done, iters, star, act, act_cnt, viol, traj, dens_prefix, cfg, total;
+  int viol_words, traj_stride;
 };
-MsLayout ms_layout(int cap, int n_fits) {
+MsLayout ms_layout(int cap, int n_fits, int max_iter) {
   MsLayout L;
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -392,11 +492,16 @@ MsLayout ms_layout(int cap, int n_fits) {
   const size_t nf = n_fits > 0 ? n_fits : 1, cp = cap > 0 ? cap : 1;
   L.cpts = take(cp * sizeof(float4));
   L.seeds = take(cp * sizeof(float4));
+  L.viol_words = (max_iter + 2 + 31) / 32;
+  L.traj_stride = max_iter + 2;
   L.best_key = take(nf * sizeof(unsigned long long));
-  L.fitmax = take(3 * nf * sizeof(unsigned));
   L.done = take(nf * sizeof(int));
   L.iters = take(nf * sizeof(int));
-  L.star = take(2 * nf * sizeof(float));
+  L.star = take(nf * sizeof(int));
+  L.act = take(3 * cp * sizeof(int));
+  L.act_cnt = take(3 * nf * sizeof(int));
+  L.viol = take(nf * L.viol_words * sizeof(unsigned));
+  L.traj = take(nf * static_cast<size_t>(L.traj_stride) * sizeof(float4));
   L.dens_prefix = take((nf + 1) * sizeof(int));
   L.cfg = take(16 * sizeof(int));
   L.total = off;
@@ -436,7 +541,7 @@ int meanshift_launch(const float4 *pts, const int *fit_start, const int *fit_cou
   int rc = ms_persistent_grid(&grid);
   if (rc != PVN3D_OK) return rc;
   const float bwf = static_cast<float>(bandwidth);
-  const MsLayout L = ms_layout(cap, n_fits);
+  const MsLayout L = ms_layout(cap, n_fits, max_iter);
   for (int f0 = 0; f0 < n_fits; f0 += kMsFitMax) {
     const int nf = std::min(kMsFitMax, n_fits - f0);
     MsArgs a;
@@ -457,13 +562,18 @@ int meanshift_launch(const float4 *pts, const int *fit_start, const int *fit_cou
     a.cpts = reinterpret_cast<float4 *>(ws + L.cpts);
     a.seeds = reinterpret_cast<float4 *>(ws + L.seeds);
     a.best_key = reinterpret_cast<unsigned long long *>(ws + L.best_key) + f0;
-    a.fitmax = reinterpret_cast<unsigned *>(ws + L.fitmax) + 3 * static_cast<size_t>(f0);
     a.done = reinterpret_cast<int *>(ws + L.done) + f0;
     a.iters = reinterpret_cast<int *>(ws + L.iters) + f0;
-    a.star_shift = reinterpret_cast<float *>(ws + L.star) + 2 * static_cast<size_t>(f0);
+    a.star_it = reinterpret_cast<int *>(ws + L.star) + f0;
+    a.act = reinterpret_cast<int *>(ws + L.act);
+    a.act_cnt = reinterpret_cast<int *>(ws + L.act_cnt) + 3 * static_cast<size_t>(f0);
+    a.viol = reinterpret_cast<unsigned *>(ws + L.viol) + static_cast<size_t>(f0) * L.viol_words;
+    a.traj = reinterpret_cast<float4 *>(ws + L.traj) + static_cast<size_t>(f0) * L.traj_stride;
     a.dens_prefix = reinterpret_cast<int *>(ws + L.dens_prefix);
     a.cfg = reinterpret_cast<int *>(ws + L.cfg);
-    a.grid_ctas = grid;
+    a.cap = cap;
+    a.viol_words = L.viol_words;
+    a.traj_stride = L.traj_stride;
 
     ms_setup_kernel<<<1, 1024, 0, st>>>(a);
     if ((rc = check_launch("ms_setup_kernel")) != PVN3D_OK) return rc;
@@ -483,12 +593,15 @@ int meanshift_launch(const float4 *pts, const int *fit_start, const int *fit_cou
   return PVN3D_OK;
 }
 
-size_t meanshift_ws_bytes(int cap, int n_fits) { return ms_layout(cap, n_fits).total; }
+size_t meanshift_ws_bytes(int cap, int n_fits, int max_iter) {
+  return ms_layout(cap, n_fits, max_iter).total;
+}
 
 }  // namespace pvn3d
 
-extern "C" size_t pvn3d_meanshift_workspace_bytes(int cap, int n_fits) {
-  return pvn3d::meanshift_ws_bytes(cap, n_fits);
+extern "C" size_t pvn3d_meanshift_workspace_bytes(int cap, int n_fits, int max_iter) {
+  if (cap < 0 || n_fits < 0 || max_iter < 0 || max_iter > 4094) return 0;
+  return pvn3d::meanshift_ws_bytes(cap, n_fits, max_iter);
 }
 
 extern "C" int pvn3d_meanshift_fit_batch(const float *pts, const int *fit_start,
@@ -500,7 +613,8 @@ extern "C" int pvn3d_meanshift_fit_batch(const float *pts, const int *fit_start,
   if (!pts || !fit_start || !fit_count || !ctr || !max_idx || !n_in || !workspace || n_fits < 0 ||
       cap < 0 || !(bandwidth > 0.0) || max_iter < 0)
     return PVN3D_ERR_INVALID_ARG;
-  if (workspace_bytes < meanshift_ws_bytes(cap, n_fits)) return PVN3D_ERR_WORKSPACE;
+  if (max_iter > 4094) return PVN3D_ERR_UNSUPPORTED;
+  if (workspace_bytes < meanshift_ws_bytes(cap, n_fits, max_iter)) return PVN3D_ERR_WORKSPACE;
   if ((reinterpret_cast<uintptr_t>(pts) & 15u) || (reinterpret_cast<uintptr_t>(ctr) & 15u) ||
       (reinterpret_cast<uintptr_t>(workspace) & 255u))
     return PVN3D_ERR_INVALID_ARG;

@@ -18,7 +18,7 @@ namespace pvn3d {
 int meanshift_launch(const float4 *pts, const int *fit_start, const int *fit_count, int n_fits,
                      int cap, double bandwidth, int max_iter, unsigned flags, float4 *ctr,
                      uint8_t *labels, int *max_idx, int *n_in, unsigned char *ws, cudaStream_t st);
-size_t meanshift_ws_bytes(int cap, int n_fits);
+size_t meanshift_ws_bytes(int cap, int n_fits, int max_iter);
 
 namespace {
 
@@ -438,7 +438,7 @@ struct PoseLayout {
   size_t perm, cls_off, perm2, cls_off2, new_mask, fs_ctr, fc_ctr, fs_kp, fc_kp, ctr1, ctr2, kp_ctr,
       mi, ni, labels, sel_pos, sel_base, pts_ctr, pts_kp, present, ms, total;
 };
-PoseLayout pose_layout(int b, int n, int k, int n_cls) {
+PoseLayout pose_layout(int b, int n, int k, int n_cls, int max_iter) {
   PoseLayout L;
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -467,7 +467,7 @@ PoseLayout pose_layout(int b, int n, int k, int n_cls) {
   L.pts_ctr = take(bn * 16);
   L.pts_kp = take(bn * k * 16);
   L.present = take(bc);
-  L.ms = take(meanshift_ws_bytes(static_cast<int>(bn * k), static_cast<int>(bc * k)));
+  L.ms = take(meanshift_ws_bytes(static_cast<int>(bn * k), static_cast<int>(bc * k), max_iter));
   L.total = off;
   return L;
 }
@@ -485,9 +485,10 @@ extern "C" int pvn3d_best_fit_transform_batch(const float *a, const float *b, co
   return check_launch("best_fit_kernel");
 }
 
-extern "C" size_t pvn3d_frame_poses_workspace_bytes(int b, int n, int k, int n_cls) {
-  if (b <= 0 || n <= 0 || k <= 0 || n_cls <= 0) return 0;
-  return pose_layout(b, n, k, n_cls).total;
+extern "C" size_t pvn3d_frame_poses_workspace_bytes(int b, int n, int k, int n_cls, int max_iter) {
+  if (b <= 0 || n <= 0 || k <= 0 || n_cls <= 0 || max_iter < 0 || max_iter > 4094) return 0;
+  if (static_cast<long long>(b) * n * k > 0x7fffffffll) return 0;
+  return pose_layout(b, n, k, n_cls, max_iter).total;
 }
 
 extern "C" int pvn3d_frame_poses_batch(const float *pcld, const int *mask, const float *ctr_of,
@@ -504,7 +505,8 @@ extern "C" int pvn3d_frame_poses_batch(const float *pcld, const int *mask, const
   if (b == 0) return PVN3D_OK;
   if (n_cls > kMaxCls || k > kMaxKabschPts || b > 65535) return PVN3D_ERR_UNSUPPORTED;
   if (static_cast<long long>(b) * n * k > 0x7fffffffll) return PVN3D_ERR_UNSUPPORTED;
-  const PoseLayout L = pose_layout(b, n, k, n_cls);
+  if (max_iter < 0 || max_iter > 4094) return PVN3D_ERR_UNSUPPORTED;
+  const PoseLayout L = pose_layout(b, n, k, n_cls, max_iter);
   if (workspace_bytes < L.total) return PVN3D_ERR_WORKSPACE;
   if (reinterpret_cast<uintptr_t>(workspace) & 255u) return PVN3D_ERR_INVALID_ARG;
   unsigned char *ws = static_cast<unsigned char *>(workspace);

@@ -45,7 +45,7 @@ class FramePoseSolver:
             self.cls_radius = torch.from_numpy(np.ascontiguousarray(cls_radius, dtype=np.float32)).to(self.dev)
         self.bandwidth, self.max_iter = float(bandwidth), int(max_iter)
         self.flags = PVN3D_MS_EARLY_EXIT if early_exit else PVN3D_MS_STRICT
-        self.ws_bytes = int(self.lib.pvn3d_frame_poses_workspace_bytes(self.b, self.n, self.k, self.n_cls))
+        self.ws_bytes = int(self.lib.pvn3d_frame_poses_workspace_bytes(self.b, self.n, self.k, self.n_cls, self.max_iter))
         self._ws = torch.empty((self.ws_bytes + 256,), dtype=torch.uint8, device=self.dev)
         self._ws_ptr = (self._ws.data_ptr() + 255) // 256 * 256
         self.poses = torch.empty((self.b, self.n_cls, 3, 4), dtype=torch.float32, device=self.dev)

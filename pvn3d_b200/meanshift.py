@@ -18,17 +18,21 @@ from typing import List, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import PVN3D_MS_EARLY_EXIT, PVN3D_MS_STRICT, check, ptr
+from ._lib import PVN3D_MS_EARLY_EXIT, PVN3D_MS_NO_FREEZE, PVN3D_MS_STRICT, check, ptr
 
 
 class MeanShiftTorch:
-    def __init__(self, bandwidth: float = 0.05, max_iter: int = 300, early_exit: bool = False):
+    def __init__(self, bandwidth: float = 0.05, max_iter: int = 300, early_exit: bool = False,
+                 no_freeze: bool = False):
         self.bandwidth = bandwidth
         self.stop_thresh = bandwidth * 1e-3  # meanshift_pytorch.py:21 (informational; kernel derives it)
         self.max_iter = max_iter
         #: PVN3D_MS_EARLY_EXIT also stops a fit once the RETURNED seed is stationary to 1e-6*bandwidth
         #: (same centre to ~1e-7 m, fewer sweeps).  Default is the reference's global stop rule.
         self.early_exit = early_exit
+        #: validation switch: sweep every seed at every iteration like the reference does, instead of
+        #: dropping seeds that have stopped moving (shift < 1e-6*bandwidth) from the work lists
+        self.no_freeze = no_freeze
         self.last_iters = None  # iteration count(s) of the last call, device tensor
 
     # ---- reference surface -------------------------------------------------------------------
@@ -75,10 +79,12 @@ class MeanShiftTorch:
         labels = torch.empty((cap,), dtype=torch.uint8, device=dev) if want_labels else None
         max_idx = torch.empty((nf,), dtype=torch.int32, device=dev)
         n_in = torch.empty((nf,), dtype=torch.int32, device=dev)
-        ws_bytes = lib.pvn3d_meanshift_workspace_bytes(cap, nf)
+        ws_bytes = lib.pvn3d_meanshift_workspace_bytes(cap, nf, int(self.max_iter))
+        if ws_bytes == 0:
+            raise ValueError("max_iter must be in [0, 4094]")
         ws = torch.empty((ws_bytes + 256,), dtype=torch.uint8, device=dev)
         ws_ptr = (ws.data_ptr() + 255) // 256 * 256
-        flags = PVN3D_MS_EARLY_EXIT if self.early_exit else PVN3D_MS_STRICT
+        flags = (PVN3D_MS_EARLY_EXIT if self.early_exit else PVN3D_MS_STRICT) | (PVN3D_MS_NO_FREEZE if self.no_freeze else 0)
         with torch.cuda.device(dev):
             rc = lib.pvn3d_meanshift_fit_batch(
                 ptr(pts4), ptr(fit_start), ptr(fit_count), nf, cap, float(self.bandwidth),

@@ -44,6 +44,7 @@ def test_no_torch_dependency_in_library():
 
 def test_workspace_queries_are_host_only():
     lib = _lib.load()
-    assert lib.pvn3d_meanshift_workspace_bytes(12288, 9) > 12288 * 32
-    assert lib.pvn3d_frame_poses_workspace_bytes(2, 2048, 8, 22) > 0
-    assert lib.pvn3d_frame_poses_workspace_bytes(0, 2048, 8, 22) == 0
+    assert lib.pvn3d_meanshift_workspace_bytes(12288, 9, 300) > 12288 * 32
+    assert lib.pvn3d_meanshift_workspace_bytes(12288, 9, 100000) == 0      # max_iter cap
+    assert lib.pvn3d_frame_poses_workspace_bytes(2, 2048, 8, 22, 300) > 0
+    assert lib.pvn3d_frame_poses_workspace_bytes(0, 2048, 8, 22, 300) == 0

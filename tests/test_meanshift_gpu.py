@@ -21,11 +21,15 @@ def _rel_err(a, b):
 
 
 @pytest.mark.parametrize("name", CASES)
-@pytest.mark.parametrize("early_exit", [False, True])
-def test_fit_matches_reference_golden(cuda_dev, golden_dir, name, early_exit):
+@pytest.mark.parametrize("mode", ["strict", "no_freeze", "early_exit"])
+def test_fit_matches_reference_golden(cuda_dev, golden_dir, name, mode):
+    """strict      = default: reference stop rule, stationary seeds dropped from the work lists
+    no_freeze   = reference stop rule, every seed swept at every iteration (literal reference schedule)
+    early_exit  = opt-in: stop as soon as the returned seed is stationary"""
+    early_exit = mode == "early_exit"
     z = np.load(os.path.join(golden_dir, "ms_cases.npz"))
     A = torch.from_numpy(z[f"{name}_A"]).to(cuda_dev)
-    ms = MeanShiftTorch(bandwidth=float(z[f"{name}_bw"]), early_exit=early_exit)
+    ms = MeanShiftTorch(bandwidth=float(z[f"{name}_bw"]), early_exit=early_exit, no_freeze=mode == "no_freeze")
     ctr, labels = ms.fit(A)
     assert labels.dtype == torch.bool and labels.shape == (A.size(0),) and ctr.shape == (3,)
     assert np.array_equal(labels.cpu().numpy(), z[f"{name}_labels"]), "labels must be bit-exact"
@@ -84,6 +88,32 @@ def test_properties_at_full_size(cuda_dev):
     assert float((c0.cpu() - torch.tensor([0.1, -0.05, 0.8])).norm()) < 0.003
     ce, le = MeanShiftTorch(0.08, early_exit=True).fit(At)
     assert torch.equal(le, l0) and float((ce - c0).norm() / c0.norm()) < REL_TOL
+    # dropping stationary seeds from the work lists changes neither T nor the centre
+    msn = MeanShiftTorch(0.08, no_freeze=True)
+    cn, ln = msn.fit(At)
+    assert torch.equal(ln, l0) and float((cn - c0).norm() / c0.norm()) < 1e-6
+    assert abs(int(msn.last_iters[0]) - int(ms.last_iters[0])) <= 1
+
+
+def test_multi_tile_fit_and_max_iter_cap(cuda_dev):
+    """n > 4096 points takes the streamed (multi-tile) sweep; max_iter caps the iteration count at
+    max_iter + 1 like the reference loop (it > max_iter breaks after the sweep)."""
+    rng = np.random.default_rng(2)
+    n = 6000
+    A = (np.array([0.0, 0.1, 0.9]) + rng.normal(0, 0.01, size=(n, 3))).astype(np.float32)
+    out = rng.choice(n, n // 8, replace=False)
+    A[out] = rng.uniform([-0.5, -0.4, 0.6], [0.5, 0.4, 1.2], size=(len(out), 3)).astype(np.float32)
+    At = torch.from_numpy(A).to(cuda_dev)
+    ms = MeanShiftTorch(0.08)
+    c0, l0 = ms.fit(At)
+    msn = MeanShiftTorch(0.08, no_freeze=True)
+    cn, ln = msn.fit(At)
+    assert torch.equal(l0, ln) and float((cn - c0).norm() / c0.norm()) < 1e-6
+    assert abs(int(msn.last_iters[0]) - int(ms.last_iters[0])) <= 1
+    assert float((c0.cpu() - torch.tensor([0.0, 0.1, 0.9])).norm()) < 0.005
+    capped = MeanShiftTorch(0.08, max_iter=4)
+    capped.fit(At)
+    assert int(capped.last_iters[0]) == 5
 
 
 def test_cpu_tensor_is_rejected():
