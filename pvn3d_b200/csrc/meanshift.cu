@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(kMsThreads) ms_prepare_kernel(MsArgs a) {
 // the densest input point) logs its position at every iteration, so C[max_idx] AFTER EXACTLY T
 // iterations is what comes back, as in the reference.
 //
-// Work is organised in PHASES of several iterations (6,10,16,32,64,64,...): a tile of seeds keeps
+// Work is organised in PHASES of several iterations (6,10,16,16,...): a tile of seeds keeps
 // its seeds in registers and -- when the fit has <= 4096 points -- the whole point set in shared
 // memory for the entire phase; between phases the still-moving seeds are compacted into dense
 // tiles and a grid barrier lets every CTA take the same per-fit decisions.  Typical vote sets
@@ -250,8 +250,8 @@ struct MsIterSmem {
 };
 
 __device__ __forceinline__ int ms_phase_end(int p) {  // last iteration of phase p
-  // 6, 16, 32, 64, 128, 192, 256, ...
-  return p == 0 ? 6 : p == 1 ? 16 : p == 2 ? 32 : 64 * (p - 2);
+  // 6, 16, 32, 48, 64, ... : short phases bound the work done past T (T is detected at phase ends)
+  return p == 0 ? 6 : 16 * p;
 }
 
 template <int R>
@@ -377,6 +377,129 @@ __device__ __forceinline__ void ms_run_tile(const MsArgs &a, MsIterSmem &sm, int
   }
 }
 
+// Split-sweep variant for the late phases, when only a few (creeping) seeds per fit are left: a
+// seed's iterations are inherently sequential, so with one thread per seed the critical path is
+// T * n_c pair evaluations of ONE lane.  Here a warp owns two seeds at a time and its 32 lanes share
+// the sweep (lane l takes points l, l+32, ...); the eight partial sums are combined with a butterfly
+// of warp shuffles, so every lane holds the same totals and the same new position.  Same work, 32x
+// shorter dependent chain, 32x more parallelism.
+constexpr int kMsSplitTile = 64;  // seeds per tile: 8 warps x 4 rounds x 2 seeds
+
+__device__ __forceinline__ void ms_run_tile_split(const MsArgs &a, MsIterSmem &sm, int f, int tile,
+                                                  int it_lo, int it_hi, int cur, int nxt) {
+  const int start = a.fit_start[f], n_c = a.fit_count[f];
+  const int n_act = a.act_cnt[static_cast<size_t>(cur) * a.n_fits + f];
+  const int *act_cur = a.act + static_cast<size_t>(cur) * a.cap + start;
+  int *act_nxt = a.act + static_cast<size_t>(nxt) * a.cap + start;
+  const int t = threadIdx.x;
+  const unsigned lane = t & 31u, warp = t >> 5;
+  const float k = a.kexp;
+  const bool single = n_c <= kMsPtTile;
+  const bool freeze_on = !(a.flags & PVN3D_MS_NO_FREEZE);
+  const int star = a.max_idx[f];
+
+  __syncthreads();
+  if (single) {
+    for (int q = t; q < n_c; q += kMsThreads) sm.pts[q] = a.cpts[start + q];
+    __syncthreads();
+  }
+  // multi-tile fits need CTA-wide barriers inside the sweep, so all warps walk the rounds together
+  for (int round = 0; round < kMsSplitTile / (2 * kMsWarps); ++round) {
+    int idx[2];
+    float cx[2], cy[2], cz[2], last[2];
+    bool frozen[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int pos = tile * kMsSplitTile + round * (2 * kMsWarps) + 2 * warp + r;
+      const bool valid = pos < n_act;
+      idx[r] = valid ? act_cur[pos] : -1;
+      const float4 c = a.seeds[start + (valid ? idx[r] : 0)];
+      cx[r] = c.x; cy[r] = c.y; cz[r] = c.z; last[r] = c.w;
+      frozen[r] = !valid;
+    }
+    for (int it = it_lo; it <= it_hi; ++it) {
+      const bool warp_live = !(frozen[0] && frozen[1]);  // warp-uniform
+      if (single && !warp_live) break;
+      float qx[2], qy[2], qz[2], qw[2], sw[2], sx[2], sy[2], sz[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        qx[r] = -2.f * k * cx[r];
+        qy[r] = -2.f * k * cy[r];
+        qz[r] = -2.f * k * cz[r];
+        qw[r] = k * (cx[r] * cx[r] + cy[r] * cy[r] + cz[r] * cz[r]);
+        sw[r] = sx[r] = sy[r] = sz[r] = 0.f;
+      }
+      for (int base = 0; base < n_c; base += kMsPtTile) {
+        const int n = min(kMsPtTile, n_c - base);
+        if (!single) {
+          __syncthreads();
+          for (int q = t; q < n; q += kMsThreads) sm.pts[q] = a.cpts[start + base + q];
+          __syncthreads();
+        }
+        if (warp_live) {
+#pragma unroll 4
+          for (int j = lane; j < n; j += 32) {
+            const float4 p = sm.pts[j];
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              const float e = fmaf(p.x, qx[r], fmaf(p.y, qy[r], fmaf(p.z, qz[r], p.w + qw[r])));
+              const float w = ex2_approx(e);
+              sw[r] += w;
+              sx[r] = fmaf(w, p.x, sx[r]);
+              sy[r] = fmaf(w, p.y, sy[r]);
+              sz[r] = fmaf(w, p.z, sz[r]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          sw[r] += __shfl_xor_sync(0xffffffffu, sw[r], o);
+          sx[r] += __shfl_xor_sync(0xffffffffu, sx[r], o);
+          sy[r] += __shfl_xor_sync(0xffffffffu, sy[r], o);
+          sz[r] += __shfl_xor_sync(0xffffffffu, sz[r], o);
+        }
+      }
+      bool violates = false;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        if (!frozen[r]) {
+          const float nx = __fdiv_rn(sx[r], sw[r]), ny = __fdiv_rn(sy[r], sw[r]),
+                      nz = __fdiv_rn(sz[r], sw[r]);
+          const float sh = __fsqrt_rn(torch_sqnorm(nx - cx[r], ny - cy[r], nz - cz[r]));
+          cx[r] = nx; cy[r] = ny; cz[r] = nz; last[r] = sh;
+          violates |= !(sh < a.stop_thresh);
+          const bool still = sh < a.eps_stat;
+          if (idx[r] == star && lane == 0) {
+            a.traj[static_cast<size_t>(f) * a.traj_stride + it] = make_float4(nx, ny, nz, sh);
+            if (still && a.star_it[f] == 0) a.star_it[f] = it;
+          }
+          if (still && freeze_on) frozen[r] = true;
+        }
+      }
+      if (violates && lane == 0)
+        atomicOr(a.viol + static_cast<size_t>(f) * a.viol_words + (it >> 5), 1u << (it & 31));
+      if (!single) {
+        if (!__syncthreads_or((frozen[0] && frozen[1]) ? 0 : 1)) break;
+      }
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        if (idx[r] >= 0) {
+          a.seeds[start + idx[r]] = make_float4(cx[r], cy[r], cz[r], last[r]);
+          if (!frozen[r]) {
+            const int at = atomicAdd(a.act_cnt + static_cast<size_t>(nxt) * a.n_fits + f, 1);
+            act_nxt[at] = idx[r];
+          }
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kMsThreads, 3) ms_iterate_kernel(MsArgs a) {
   extern __shared__ __align__(16) unsigned char ms_smem_raw[];
   MsIterSmem &sm = *reinterpret_cast<MsIterSmem *>(ms_smem_raw);
@@ -422,10 +545,12 @@ __global__ void __launch_bounds__(kMsThreads, 3) ms_iterate_kernel(MsArgs a) {
     int total_seeds;
     (void)block_exclusive_scan<kMsThreads>(local_seeds, sm.warp_scan, &total_seeds);
     if (total_seeds == 0 || it_lo > last_it) break;  // identical in every CTA
-    // seeds per thread: keep >= 2 tiles per CTA of the grid when there is enough work
+    // seeds per thread: keep >= 2 tiles per CTA of the grid when there is enough work; with less than
+    // one full tile per CTA left, switch to the split sweep (a warp per pair of seeds)
     int R = 2;
     if (total_seeds / (kMsThreads * R) < 2 * static_cast<int>(gridDim.x)) R = 1;
-    const int tile_seeds = kMsThreads * R;
+    const bool split = total_seeds < kMsThreads * static_cast<int>(gridDim.x);
+    const int tile_seeds = split ? kMsSplitTile : kMsThreads * R;
     int local_tiles = 0;
     for (int f = f_lo; f < f_hi; ++f) local_tiles += (sm.prefix[f] + tile_seeds - 1) / tile_seeds;
     int total;
@@ -448,7 +573,8 @@ __global__ void __launch_bounds__(kMsThreads, 3) ms_iterate_kernel(MsArgs a) {
       if (tk >= total) break;
       const int f = find_segment(sm.prefix, a.n_fits, tk);
       const int tile = tk - sm.prefix[f];
-      if (R == 2) ms_run_tile<2>(a, sm, f, tile, it_lo, it_hi, cur, nxt);
+      if (split) ms_run_tile_split(a, sm, f, tile, it_lo, it_hi, cur, nxt);
+      else if (R == 2) ms_run_tile<2>(a, sm, f, tile, it_lo, it_hi, cur, nxt);
       else ms_run_tile<1>(a, sm, f, tile, it_lo, it_hi, cur, nxt);
     }
     grid.sync();
