@@ -108,3 +108,26 @@ def test_frame_shard_and_gather_gloo_world2(n_frames):
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res) and all(mx == 2.0 for _, _, mx in res)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/pvn3d"), reason="reference checkout not present")
+def test_unmodified_reference_binds_to_the_drop_in():
+    """`from lib.pointnet2_utils import _ext` (reference pointnet2_utils.py:19) resolves to this package's
+    module, and the post-processing names are rebound -- run in a subprocess to keep sys.modules clean."""
+    import subprocess
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "from pvn3d_b200 import compat, _ext, meanshift\n"
+        "compat.install('/root/reference/pvn3d', patch_post=True)\n"
+        "from lib.pointnet2_utils import pointnet2_utils as pu\n"
+        "from lib.utils import pvn3d_eval_utils as ev, meanshift_pytorch as ms\n"
+        "from lib.pvn3d import Pointnet2MSG\n"
+        "import torch\n"
+        "assert pu._ext is _ext and ms.MeanShiftTorch is meanshift.MeanShiftTorch\n"
+        "assert ev.cal_frame_poses.__module__ == 'pvn3d_b200.eval_utils'\n"
+        "m = Pointnet2MSG(input_channels=6)\n"
+        "try:\n    m(torch.zeros(1, 4096, 9)); raise SystemExit(3)\n"
+        "except RuntimeError as e:\n    assert 'CPU not supported' in str(e)\n"
+        "print('ok')\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]

@@ -152,3 +152,40 @@ def test_group_gather_interpolate_kat():
     go = np.ones((1, 2, 2, 2), np.float32)
     gg = pn2.group_points_grad(go, idx, 5)
     assert gg[0, 0].tolist() == [1, 0, 2, 0, 1]
+
+
+def test_pn2_oracle_matches_reference_gpu_recording(golden_dir):
+    """tests/golden/pn2_ref.npz = outputs of the UNMODIFIED reference op library (oracle/_ref/_ext.so) on a
+    B200 (tests/golden/make_golden_gpu.py).  This pins the C oracle to the reference bit for bit."""
+    path = os.path.join(golden_dir, "pn2_ref.npz")
+    if not os.path.exists(path):
+        pytest.skip("pn2_ref.npz not recorded yet")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("mk", os.path.join(golden_dir, "make_golden_gpu.py"))
+    mk = importlib.util.module_from_spec(spec)
+    sys_path = list(__import__("sys").path)
+    spec.loader.exec_module(mk)
+    __import__("sys").path[:] = sys_path
+    z = np.load(path)
+    xyz, feats = mk.inputs()
+    S = mk.SPEC
+    lvl = xyz
+    for i, m in enumerate(S["fps_m"]):
+        idx = pn2.furthest_point_sampling(lvl, m)
+        assert np.array_equal(idx, z[f"fps{i}"]), f"FPS level {i}"
+        nxt = np.take_along_axis(lvl, idx[..., None].astype(np.int64).repeat(3, -1), 1)
+        assert np.array_equal(nxt, z[f"new_xyz{i}"])
+        if i == 0:
+            for j, (r, ns) in enumerate(S["bq"]):
+                bq = pn2.ball_query(nxt, lvl, float(np.float32(r)), ns)
+                assert np.array_equal(bq, z[f"bq{j}"]), f"ball_query {j}"
+                if j == 0:
+                    assert np.array_equal(pn2.group_points(feats, bq), z["group0"])
+            d2, nn = pn2.three_nn(lvl, nxt)
+            assert np.array_equal(nn, z["nn_idx"]) and np.array_equal(d2, z["nn_d2"])
+            rng = np.random.default_rng(1)
+            pf = rng.normal(size=(1, S["c_interp"], m)).astype(np.float32)
+            w = rng.uniform(size=(1, S["n"], 3)).astype(np.float32)
+            w /= w.sum(-1, keepdims=True)
+            assert np.array_equal(pn2.three_interpolate(pf, nn, w), z["interp"])
+        lvl = nxt
