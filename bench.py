@@ -141,6 +141,8 @@ def main():
     ap.add_argument("--config", default="linemod", choices=list(CONFIGS))
     ap.add_argument("--early-exit", action="store_true", help="mean-shift early exit (see DESIGN.md section 5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--engine", default="fused", choices=["fused", "modules"],
+                    help="hot path A: fused tcgen05 engine (default) or module graph with cuDNN/cuBLAS MLPs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3 if args.impl == "b200" else 0)
     cfg = CONFIGS[args.config]
@@ -191,7 +193,8 @@ def main():
     lm_obj = 1   # 'ape': one LineMOD object per batch (cal_frame_poses_lm takes a single obj_id)
     kw = dict(lm_obj_id=lm_obj) if cfg["shape"] == "linemod" else {}
     frames = synth.make_batch(cfg["shape"], B, n_points=N_POINTS, config_id=cfg["config_id"], first_frame=rank * B, **kw)
-    pipe = FramePipeline(cfg["shape"], B, n_points=N_POINTS, device=dev, lm_obj_id=lm_obj, early_exit=args.early_exit)
+    pipe = FramePipeline(cfg["shape"], B, n_points=N_POINTS, device=dev, lm_obj_id=lm_obj, early_exit=args.early_exit,
+                         engine=args.engine)
     host = synth.stack(frames)
     n_rot = 4
     host_rot = [FramePipeline.pin_batch({k: np.roll(v, 8 * r, axis=0) for k, v in host.items()}) for r in range(n_rot)]
@@ -263,7 +266,7 @@ def main():
     torch.cuda.synchronize(dev)
     ev[0].record()
     with torch.no_grad():
-        pipe.model(d["cld_rgb_nrm"])
+        (pipe.fused if pipe.fused is not None else pipe.model)(d["cld_rgb_nrm"])
     ev[1].record()
     pipe.solver.solve(d["pcld"], d["labels"], d["ctr_of"], d["kp_of"])
     ev[2].record()
@@ -284,7 +287,8 @@ def main():
                 "config": {"workload": workload, "n_points": N_POINTS, "global_batch": B * world,
                            "parallelism": f"frame-sharded x{world}, one NCCL all_gather of poses per step" if world > 1 else "1 GPU",
                            "l2": f"{n_rot} rotating device-resident input batches ({rot_bytes / 1e6:.0f} MB) > L2",
-                           "mlp": "cuDNN/cuBLAS 1x1 conv (TF32 allowed, as the reference's torch default)",
+                           "mlp": ("tcgen05.mma kind::tf32 shared-MLP layers, grouping/interpolation fused into the operand producer"
+                                   if args.engine == "fused" else "cuDNN/cuBLAS 1x1 conv (TF32 allowed, the reference's torch default)"),
                            "meanshift": "early-exit" if args.early_exit else "strict (reference global stop rule)"},
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": pipe.h2d_bytes(),
                         "d2h_bytes_per_step": pipe.d2h_bytes(), "ms_per_step": ms_e2e / args.steps},

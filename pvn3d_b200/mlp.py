@@ -1,0 +1,204 @@
+"""Hot path A on the library's own kernels end to end: FusedPointnet2MSG.
+
+Takes a Pointnet2MSG module (this package's mirror or the reference's -- same state_dict layout),
+folds every Conv2d(1x1, no bias) + BatchNorm2d (eval) pair into a TF32-rounded, zero-padded weight
+matrix + bias, and runs `Pointnet2MSG.forward` (reference pvn3d/lib/pvn3d.py:126-154) as:
+
+  per SA level : furthest_point_sampling -> (per scale) ball_query -> first SharedMLP layer with the
+                 grouping fused into the tensor-core operand producer (pvn3d_mlp_sa_first) -> middle
+                 layer (pvn3d_mlp_dense) -> last layer with ReLU + max-pool over nsample fused into the
+                 epilogue, written straight into the level's point-major feature table
+  per FP level : three_nn -> inverse-distance weights -> first layer with three_interpolate + concat
+                 fused into the producer (pvn3d_mlp_fp_first) -> second layer
+  last         : [B,N,128] -> [B,128,N] (the layout the reference returns)
+
+The grouped tensors [B,3+C,M,S] and the interpolated tensors [B,C,n] are never materialised; no
+cuDNN / cuBLAS / ATen kernel runs in this path.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Tuple
+
+import torch
+
+from . import _ext, _lib
+from ._lib import check, ptr
+from .pointnet2 import SA_SPEC
+
+
+def tf32_round(x: torch.Tensor) -> torch.Tensor:
+    """round-to-nearest (ties away) to TF32's 10-bit mantissa, like cvt.rna.tf32.f32"""
+    i = x.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def fold_conv_bn(layer: torch.nn.Module) -> Tuple[torch.Tensor, torch.Tensor]:
+    """layer = Sequential(conv [, normlayer.bn], activation) of SharedMLP (pytorch_utils.py:80-134).
+    Returns (W [N,K], bias [N]) with the eval-mode BatchNorm folded in."""
+    w = layer.conv.weight.detach().double().flatten(1)
+    n = w.size(0)
+    bias = layer.conv.bias.detach().double() if layer.conv.bias is not None else torch.zeros(n, dtype=torch.float64, device=w.device)
+    if hasattr(layer, "normlayer"):
+        bn = layer.normlayer.bn
+        scale = bn.weight.detach().double() / torch.sqrt(bn.running_var.detach().double() + bn.eps)
+        w = w * scale[:, None]
+        bias = (bias - bn.running_mean.detach().double()) * scale + bn.bias.detach().double()
+    return w.float(), bias.float()
+
+
+class PackedLayer:
+    """one folded layer in the layout pvn3d_mlp_* expects"""
+
+    def __init__(self, w: torch.Tensor, bias: torch.Tensor, k_valid_prev_pad: int | None = None):
+        n, k = w.shape
+        self.n, self.k = n, k
+        self.n_pad = (n + 15) // 16 * 16
+        k_in = k if k_valid_prev_pad is None else k_valid_prev_pad     # width of the producing activation
+        self.k_pad = (max(k, k_in) + 31) // 32 * 32
+        wp = torch.zeros((self.n_pad, self.k_pad), dtype=torch.float32, device=w.device)
+        wp[:n, :k] = w
+        self.w = tf32_round(wp).contiguous()
+        self.bias = torch.zeros((self.n_pad,), dtype=torch.float32, device=w.device)
+        self.bias[:n] = bias
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def mlp_dense(a2d: torch.Tensor, layer: PackedLayer, relu=True, pool=0, out=None, col0=0):
+    """a2d [rows, lda] point-major activations (all lda columns valid or zero)."""
+    lib = _lib.load()
+    rows, lda = a2d.shape
+    if out is None:
+        out = torch.empty((rows // pool if pool else rows, layer.n_pad), dtype=torch.float32, device=a2d.device)
+    with torch.cuda.device(a2d.device):
+        rc = lib.pvn3d_mlp_dense(ptr(a2d), lda, lda, rows, ptr(layer.w), ptr(layer.bias), layer.k_pad, layer.n_pad,
+                                 1 if relu else 0, pool, ptr(out), out.size(-1), col0, _stream(a2d.device))
+    check(rc, "pvn3d_mlp_dense")
+    return out
+
+
+def mlp_sa_first(xyz, new_xyz, feat_pm, ldf, c_feat, idx, layer: PackedLayer, relu=True, pool=0, out=None, col0=0):
+    lib = _lib.load()
+    b, n = xyz.shape[0], xyz.shape[1]
+    m, ns = idx.shape[1], idx.shape[2]
+    rows = b * m * ns
+    if out is None:
+        out = torch.empty((rows // pool if pool else rows, layer.n_pad), dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        rc = lib.pvn3d_mlp_sa_first(ptr(xyz), ptr(new_xyz), feat_pm, ldf, c_feat, ptr(idx), b, n, m, ns, ptr(layer.w),
+                                    ptr(layer.bias), layer.k_pad, layer.n_pad, 1 if relu else 0, pool, ptr(out),
+                                    out.size(-1), col0, _stream(xyz.device))
+    check(rc, "pvn3d_mlp_sa_first")
+    return out
+
+
+def mlp_fp_first(known_feat_pm, nn_idx, nn_w, skip_ptr, lds, c1, layer: PackedLayer, relu=True):
+    lib = _lib.load()
+    b, m_known, c2 = known_feat_pm.shape
+    n_unknown = nn_idx.shape[1]
+    out = torch.empty((b * n_unknown, layer.n_pad), dtype=torch.float32, device=known_feat_pm.device)
+    with torch.cuda.device(known_feat_pm.device):
+        rc = lib.pvn3d_mlp_fp_first(ptr(known_feat_pm), c2, ptr(nn_idx), ptr(nn_w), skip_ptr, lds, c1, b, n_unknown,
+                                    m_known, ptr(layer.w), ptr(layer.bias), layer.k_pad, layer.n_pad, 1 if relu else 0,
+                                    ptr(out), out.size(-1), 0, _stream(known_feat_pm.device))
+    check(rc, "pvn3d_mlp_fp_first")
+    return out
+
+
+def three_nn_weights(dist2: torch.Tensor) -> torch.Tensor:
+    lib = _lib.load()
+    w = torch.empty_like(dist2)
+    rows = dist2.numel() // 3
+    with torch.cuda.device(dist2.device):
+        rc = lib.pvn3d_three_nn_weights(ptr(dist2), rows, ptr(w), _stream(dist2.device))
+    check(rc, "pvn3d_three_nn_weights")
+    return w
+
+
+class FusedPointnet2MSG:
+    """Inference engine for Pointnet2MSG on libpvn3d_b200 only (see module docstring)."""
+
+    def __init__(self, model: torch.nn.Module, device="cuda"):
+        self.dev = torch.device(device)
+        model = model.to(self.dev).eval()
+        self.sa: List[List[List[PackedLayer]]] = []
+        self.sa_out: List[int] = []
+        for li, sa in enumerate(model.SA_modules):
+            scales = []
+            for mlp in sa.mlps:
+                layers = []
+                prev_pad = None
+                for k, layer in enumerate(mlp):
+                    w, bias = fold_conv_bn(layer)
+                    if k == 0:   # reference column order is [xyz(3) | features]; the producer emits [features | xyz]
+                        w = torch.cat([w[:, 3:], w[:, :3]], dim=1)
+                    pl = PackedLayer(w, bias, prev_pad)
+                    prev_pad = pl.n_pad
+                    layers.append(pl)
+                scales.append(layers)
+            self.sa.append(scales)
+            self.sa_out.append(sum(s[-1].n for s in scales))
+            assert all(s[-1].n % 4 == 0 for s in scales)
+        self.fp: List[List[PackedLayer]] = []
+        for fp in model.FP_modules:
+            layers, prev_pad = [], None
+            for layer in fp.mlp:
+                w, bias = fold_conv_bn(layer)
+                pl = PackedLayer(w, bias, prev_pad)
+                prev_pad = pl.n_pad
+                layers.append(pl)
+            self.fp.append(layers)
+
+    @torch.no_grad()
+    def forward(self, pointcloud: torch.Tensor) -> torch.Tensor:
+        """pointcloud [B,N,3+C] f32 contiguous on device -> features [B,128,N] (as the reference returns)"""
+        assert pointcloud.is_cuda and pointcloud.is_contiguous() and pointcloud.dtype == torch.float32
+        b, n0, width = pointcloud.shape
+        c0 = width - 3
+        xyz = pointcloud[..., :3].contiguous()
+        # level-0 descriptors are columns 3.. of the input rows themselves (point-major already)
+        feats: List[Tuple[int, int, int]] = [(pointcloud.data_ptr() + 12, width, c0)]   # (address, ld, channels)
+        keep = [pointcloud]
+        l_xyz = [xyz]
+        for li, (npoint, radii, nsamples, _) in enumerate(SA_SPEC):
+            x = l_xyz[-1]
+            fptr, ldf, c_feat = feats[-1]
+            fidx = _ext.furthest_point_sampling(x, npoint)
+            new_xyz = torch.gather(x, 1, fidx.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
+            out_l = torch.empty((b, npoint, self.sa_out[li]), dtype=torch.float32, device=self.dev)
+            col = 0
+            for (r, ns, layers) in zip(radii, nsamples, self.sa[li]):
+                idx = _ext.ball_query(new_xyz, x, r, ns)
+                h = mlp_sa_first(x, new_xyz, fptr, ldf, c_feat, idx, layers[0])
+                for mid in layers[1:-1]:
+                    h = mlp_dense(h, mid)
+                mlp_dense(h, layers[-1], pool=ns, out=out_l.view(b * npoint, -1), col0=col)
+                col += layers[-1].n
+            l_xyz.append(new_xyz)
+            feats.append((out_l.data_ptr(), out_l.size(-1), out_l.size(-1)))
+            keep.append(out_l)
+        # feature propagation, deepest first (pvn3d.py:149-152)
+        l_feat = list(keep)            # l_feat[i]: tensor owning level i's descriptors (point-major)
+        for i in range(3, -1, -1):
+            unknown, known = l_xyz[i], l_xyz[i + 1]
+            d2, nn_idx = _ext.three_nn(unknown, known)
+            nn_w = three_nn_weights(d2)
+            known_feat = l_feat[i + 1]
+            if known_feat.dim() == 2:
+                known_feat = known_feat.view(b, known.size(1), -1)
+            sptr, lds, c1 = feats[i]
+            layers = self.fp[i]
+            h = mlp_fp_first(known_feat, nn_idx, nn_w, sptr, lds, c1, layers[0])
+            for lyr in layers[1:]:
+                h = mlp_dense(h, lyr)
+            l_feat[i] = h.view(b, unknown.size(1), -1)
+            feats[i] = (h.data_ptr(), h.size(-1), h.size(-1))
+        out_pm = l_feat[0]
+        n_out = self.fp[0][-1].n
+        if out_pm.size(-1) != n_out:
+            out_pm = out_pm[..., :n_out].contiguous()
+        return _ext.transpose_nc_to_cn(out_pm)
+
+    __call__ = forward

@@ -17,16 +17,22 @@ import torch
 
 from . import fixtures
 from .eval_utils import FramePoseSolver
+from .mlp import FusedPointnet2MSG
 from .testing import seeded_pointnet2msg
 
 
 class FramePipeline:
     def __init__(self, shape: str, batch: int, n_points: int = fixtures.N_SAMPLE_POINTS, device="cuda",
                  lm_obj_id: int = 1, early_exit: bool = False, model: Optional[torch.nn.Module] = None,
-                 allow_tf32: bool = True):
+                 allow_tf32: bool = True, engine: str = "fused"):
         self.dev = torch.device(device)
         self.shape, self.b, self.n, self.k = shape, int(batch), int(n_points), fixtures.N_KEYPOINTS
         self.model = (model if model is not None else seeded_pointnet2msg(0, 1)).to(self.dev).eval()
+        #: "fused"  = hot path A entirely on libpvn3d_b200 (tcgen05 shared MLPs, grouping/interpolation fused
+        #:            into the operand producers -- pvn3d_b200.mlp.FusedPointnet2MSG)
+        #: "modules" = the Pointnet2MSG module graph on the library's `_ext` ops with cuDNN/cuBLAS MLPs
+        self.engine = engine
+        self.fused = FusedPointnet2MSG(self.model, self.dev) if engine == "fused" else None
         if shape == "linemod":
             self.n_cls = 2
             mesh = fixtures.mesh_kps_table_lm(lm_obj_id)
@@ -65,12 +71,15 @@ class FramePipeline:
     @torch.no_grad()
     def run_device(self, cld_rgb_nrm, pcld, labels, ctr_of, kp_of):
         """inputs resident in HBM; returns device views (poses [B,n_cls,3,4], present [B,n_cls])."""
-        prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
-        torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = self.allow_tf32
-        try:
-            self.features = self.model(cld_rgb_nrm)                       # hot path A: [B,128,N]
-        finally:
-            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+        if self.fused is not None:
+            self.features = self.fused(cld_rgb_nrm)                       # hot path A: [B,128,N]
+        else:
+            prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = self.allow_tf32
+            try:
+                self.features = self.model(cld_rgb_nrm)
+            finally:
+                torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
         poses, present, _, _ = self.solver.solve(pcld, labels, ctr_of, kp_of)   # hot path B
         return poses, present
 

@@ -1,0 +1,118 @@
+"""The tcgen05 shared-MLP layer kernel (csrc/mlp_tc.cu) against a float64 torch reference of the same
+op on TF32-rounded operands, and the fused hot path A against features recorded from the REFERENCE
+Pointnet2MSG.  Tolerances: the kernel itself 2e-5 relative (fp32 accumulation order only); end to end
+the TF32 class of the reference's default cuDNN path (written at the assertion)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pn2
+from pvn3d_b200 import mlp, testing
+
+pytestmark = pytest.mark.gpu
+
+
+def ref_dense(a, w, b, relu, pool):
+    y = a.double() @ w.double().t() + b.double()
+    if relu:
+        y = y.clamp_min(0)
+    if pool:
+        y = y.view(-1, pool, y.size(-1)).max(1).values
+    return y.float()
+
+
+@pytest.mark.parametrize("rows,k,n,relu,pool", [
+    (128, 32, 16, False, 0), (300, 64, 64, True, 0), (1000, 96, 128, True, 0), (512, 128, 196, True, 0),
+    (512, 256, 384, True, 0), (640, 544, 256, True, 0), (2048, 384, 512, True, 32), (1024, 64, 32, True, 16),
+    (256, 32, 16, False, 8), (131, 48, 80, True, 0)])
+def test_dense_layer(cuda_dev, rows, k, n, relu, pool):
+    g = torch.Generator().manual_seed(rows + k + n)
+    a = torch.randn(rows, k, generator=g)
+    w = torch.randn(n, k, generator=g) / np.sqrt(k)
+    b = torch.randn(n, generator=g)
+    layer = mlp.PackedLayer(w.to(cuda_dev), b.to(cuda_dev))
+    lda = (k + 15) // 16 * 16
+    ad = torch.zeros(rows, lda, device=cuda_dev)
+    ad[:, :k] = a.to(cuda_dev)
+    out = mlp.mlp_dense(ad, layer, relu=relu, pool=pool).cpu()
+    want = ref_dense(mlp.tf32_round(a), mlp.tf32_round(w), b, relu, pool)
+    assert out.shape == ((rows // pool if pool else rows), layer.n_pad)
+    assert (out[:, :n] - want).abs().max() <= 2e-5 * max(1.0, want.abs().max())
+    if layer.n_pad > n:
+        assert out[:, n:].abs().max() == 0           # pad columns are exact zeros for the next layer
+
+
+def test_sa_first_layer_fuses_query_and_group(cuda_dev):
+    rng = np.random.default_rng(1)
+    b_, n_, m_, c_, ns_ = 2, 1024, 128, 96, 16
+    xyz = rng.uniform(0, 1, (b_, n_, 3)).astype(np.float32)
+    fidx = pn2.furthest_point_sampling(xyz, m_)
+    new = np.take_along_axis(xyz, fidx[..., None].astype(np.int64).repeat(3, -1), 1)
+    feats = rng.normal(size=(b_, c_, n_)).astype(np.float32)
+    grouped, idx = pn2.query_and_group(xyz, new, feats, float(np.float32(0.15)), ns_)      # [B,3+C,M,S] oracle
+    w = torch.from_numpy((rng.normal(size=(64, 3 + c_)) / 10).astype(np.float32))
+    bias = torch.from_numpy(rng.normal(size=64).astype(np.float32))
+    X = torch.from_numpy(grouped).permute(0, 2, 3, 1).reshape(-1, 3 + c_)
+    want = ref_dense(mlp.tf32_round(X), mlp.tf32_round(w), bias, True, 0)
+    layer = mlp.PackedLayer(torch.cat([w[:, 3:], w[:, :3]], 1).to(cuda_dev), bias.to(cuda_dev))
+    feat_pm = torch.from_numpy(feats).permute(0, 2, 1).contiguous().to(cuda_dev)
+    args = (torch.from_numpy(xyz).to(cuda_dev), torch.from_numpy(new).to(cuda_dev), feat_pm.data_ptr(), c_, c_,
+            torch.from_numpy(idx).to(cuda_dev), layer)
+    out = mlp.mlp_sa_first(*args).cpu()
+    assert (out[:, :64] - want).abs().max() <= 2e-5 * want.abs().max()
+    pooled = mlp.mlp_sa_first(*args, pool=ns_).cpu()
+    assert (pooled[:, :64] - want.view(-1, ns_, 64).max(1).values).abs().max() <= 2e-5 * want.abs().max()
+
+
+def test_fp_first_layer_fuses_interpolation(cuda_dev):
+    rng = np.random.default_rng(2)
+    b_, n_u, m_k, c2, c1 = 2, 512, 128, 256, 96
+    unk = rng.uniform(0, 1, (b_, n_u, 3)).astype(np.float32)
+    kn = rng.uniform(0, 1, (b_, m_k, 3)).astype(np.float32)
+    d2, nn = pn2.three_nn(unk, kn)
+    kf = torch.from_numpy(rng.normal(size=(b_, m_k, c2)).astype(np.float32))
+    sk = torch.from_numpy(rng.normal(size=(b_, n_u, c1)).astype(np.float32))
+    nw = mlp.three_nn_weights(torch.from_numpy(d2).to(cuda_dev))
+    dr = 1.0 / (torch.sqrt(torch.from_numpy(d2)) + 1e-8)                        # pointnet2_modules.py:184-186
+    wref = dr / dr.sum(2, keepdim=True)
+    assert (nw.cpu() - wref).abs().max() < 2e-7
+    interp = (kf[torch.arange(b_)[:, None, None], torch.from_numpy(nn).long()] * wref[..., None]).sum(2)
+    X = torch.cat([interp, sk], -1).reshape(-1, c2 + c1)
+    w = torch.from_numpy((rng.normal(size=(128, c2 + c1)) / 16).astype(np.float32))
+    bias = torch.from_numpy(rng.normal(size=128).astype(np.float32))
+    want = ref_dense(mlp.tf32_round(X), mlp.tf32_round(w), bias, True, 0)
+    layer = mlp.PackedLayer(w.to(cuda_dev), bias.to(cuda_dev))
+    skd = sk.to(cuda_dev)
+    out = mlp.mlp_fp_first(kf.to(cuda_dev), torch.from_numpy(nn).to(cuda_dev), nw, skd.data_ptr(), c1, c1, layer).cpu()
+    # interpolation rounds to TF32 after a 3-term fp32 sum: allow one TF32 ulp of the operands
+    assert (out[:, :128] - want).abs().max() <= 1e-3 * want.abs().max()
+
+
+def test_fused_pointnet2msg_matches_reference_features(cuda_dev, golden_dir):
+    """End to end vs the reference Pointnet2MSG (fp32 on CPU).  TF32 operands (10-bit mantissa) through
+    12 shared-MLP layers on raw 0..255 colours: mean error <= 0.3 % and max error <= 5 % of the mean
+    feature magnitude -- the same class as the module graph under torch's default TF32 convolutions,
+    which is measured alongside."""
+    z = np.load(os.path.join(golden_dir, "pn2msg.npz"))
+    model = testing.seeded_pointnet2msg(0, 1)
+    eng = mlp.FusedPointnet2MSG(model, cuda_dev)
+    x = torch.from_numpy(z["cld_rgb_nrm"])[None].to(cuda_dev)
+    y = eng(x)
+    assert y.shape == (1, 128, x.size(1))
+    cols = torch.from_numpy(z["cols"]).long().to(cuda_dev)
+    got = y[0][:, cols].cpu().numpy()
+    scale = float(z["feat_abs_mean"])
+    err = np.abs(got - z["feats"])
+    prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        with torch.no_grad():
+            y_mod = model.to(cuda_dev)(x)[0][:, cols].cpu().numpy()
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
+    err_mod = np.abs(y_mod - z["feats"])
+    print(f"fused: mean {err.mean() / scale:.2e} max {err.max() / scale:.2e} | cuDNN-TF32 modules: "
+          f"mean {err_mod.mean() / scale:.2e} max {err_mod.max() / scale:.2e}")
+    assert err.mean() <= 3e-3 * scale and err.max() <= 5e-2 * scale

@@ -31,11 +31,12 @@ def test_pointnet2msg_matches_reference_features(cuda_dev, golden_dir):
     assert np.abs(got - want).mean() <= 1e-4 * max(scale, 1.0)
 
 
+@pytest.mark.parametrize("engine", ["fused", "modules"])
 @pytest.mark.parametrize("shape,batch", [("linemod", 2), ("ycb", 2)])
-def test_frame_pipeline_recovers_synthetic_poses(cuda_dev, shape, batch):
+def test_frame_pipeline_recovers_synthetic_poses(cuda_dev, shape, batch, engine):
     n = 4096
     frames = synth.make_batch(shape, batch, n_points=n, config_id=9)
-    pipe = FramePipeline(shape, batch, n_points=n, device=cuda_dev,
+    pipe = FramePipeline(shape, batch, n_points=n, device=cuda_dev, engine=engine,
                          lm_obj_id=frames[0].obj_id if shape == "linemod" else 1)
     hb = FramePipeline.pin_batch(synth.stack(frames))
     poses, present = pipe.run_host(hb)
