@@ -659,9 +659,11 @@ int ms_persistent_grid(int *out) {
 }  // namespace
 
 // internal entry shared with poses.cu: fits already described on device, workspace carved by caller
+// density_only: stop after the exact pass (max_idx, n_in, labels); no iterations, ctr untouched
 int meanshift_launch(const float4 *pts, const int *fit_start, const int *fit_count, int n_fits,
                      int cap, double bandwidth, int max_iter, unsigned flags, float4 *ctr,
-                     uint8_t *labels, int *max_idx, int *n_in, unsigned char *ws, cudaStream_t st) {
+                     uint8_t *labels, int *max_idx, int *n_in, unsigned char *ws, cudaStream_t st,
+                     bool density_only) {
   if (n_fits <= 0) return PVN3D_OK;
   int grid = 0;
   int rc = ms_persistent_grid(&grid);
@@ -709,6 +711,7 @@ int meanshift_launch(const float4 *pts, const int *fit_start, const int *fit_cou
     if ((rc = check_launch("ms_density_kernel")) != PVN3D_OK) return rc;
     ms_prepare_kernel<<<tiles, kMsThreads, 0, st>>>(a);
     if ((rc = check_launch("ms_prepare_kernel")) != PVN3D_OK) return rc;
+    if (density_only) continue;
     void *kargs[] = {&a};
     PVN3D_CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(ms_iterate_kernel),
                                                dim3(grid), dim3(kMsThreads), kargs,
@@ -747,5 +750,5 @@ extern "C" int pvn3d_meanshift_fit_batch(const float *pts, const int *fit_start,
   return meanshift_launch(reinterpret_cast<const float4 *>(pts), fit_start, fit_count, n_fits, cap,
                           bandwidth, max_iter, flags, reinterpret_cast<float4 *>(ctr), labels,
                           max_idx, n_in, static_cast<unsigned char *>(workspace),
-                          pvn3d::as_stream(stream));
+                          pvn3d::as_stream(stream), false);
 }

@@ -17,7 +17,8 @@ namespace pvn3d {
 
 int meanshift_launch(const float4 *pts, const int *fit_start, const int *fit_count, int n_fits,
                      int cap, double bandwidth, int max_iter, unsigned flags, float4 *ctr,
-                     uint8_t *labels, int *max_idx, int *n_in, unsigned char *ws, cudaStream_t st);
+                     uint8_t *labels, int *max_idx, int *n_in, unsigned char *ws, cudaStream_t st,
+                     bool density_only);
 size_t meanshift_ws_bytes(int cap, int n_fits, int max_iter);
 
 namespace {
@@ -150,11 +151,13 @@ __global__ void relabel_kernel(const float *__restrict__ pcld, const float *__re
 
 // per frame: rank of every inlier among the inliers (compacted order), per-class selected counts,
 // and the (start,count) of every keypoint fit  f = (b*n_cls + c)*K + k.
-// Layout of the keypoint vote buffer: frame b owns rows [b*K*N, (b+1)*K*N); inside, class c starts
-// at K*S_c (S_c = inliers of lower classes) and holds K runs of n_sel_c votes.
+// Layout of the keypoint vote buffer (which follows the centre votes at row `base` of the same
+// allocation, so that one mean-shift launch can take centre AND keypoint fits): frame b owns rows
+// base + [b*K*N, (b+1)*K*N); inside, class c starts at K*S_c (S_c = inliers of lower classes) and
+// holds K runs of n_sel_c votes.
 __global__ void __launch_bounds__(kCompactThreads)
 kp_layout_kernel(const uint8_t *__restrict__ labels /*[B*N] in compacted order, or NULL = all*/,
-                 const int *__restrict__ cls_off, int n, int n_cls, int k_kp,
+                 const int *__restrict__ cls_off, int n, int n_cls, int k_kp, int base,
                  int *__restrict__ sel_pos /*[B*N]*/, int *__restrict__ sel_base /*[B*n_cls]*/,
                  int *__restrict__ fit_start, int *__restrict__ fit_count) {
   __shared__ int s_warp[kCompactThreads / 32];
@@ -208,7 +211,7 @@ kp_layout_kernel(const uint8_t *__restrict__ labels /*[B*N] in compacted order, 
     sel_base[static_cast<size_t>(b) * n_cls + c] = sc;
     for (int k = 0; k < k_kp; ++k) {
       const size_t f = (static_cast<size_t>(b) * n_cls + c) * k_kp + k;
-      fit_start[f] = b * k_kp * n + k_kp * sc + k * nsel;
+      fit_start[f] = base + b * k_kp * n + k_kp * sc + k * nsel;
       fit_count[f] = nsel;
     }
   }
@@ -452,22 +455,24 @@ PoseLayout pose_layout(int b, int n, int k, int n_cls, int max_iter) {
   L.perm2 = take(bn * 4);
   L.cls_off2 = take(static_cast<size_t>(b) * (n_cls + 1) * 4);
   L.new_mask = take(bn * 4);
-  L.fs_ctr = take(bc * 4);
-  L.fc_ctr = take(bc * 4);
-  L.fs_kp = take(bc * k * 4);
-  L.fc_kp = take(bc * k * 4);
+  // fit tables / results hold the centre fits [0, bc) followed by the keypoint fits [bc, bc + bc*k)
+  L.fs_ctr = take(bc * (k + 1) * 4);
+  L.fc_ctr = take(bc * (k + 1) * 4);
+  L.fs_kp = L.fs_ctr + bc * 4;
+  L.fc_kp = L.fc_ctr + bc * 4;
   L.ctr1 = take(bc * 16);
-  L.ctr2 = take(bc * 16);
-  L.kp_ctr = take(bc * k * 16);
-  L.mi = take(bc * k * 4);
-  L.ni = take(bc * k * 4);
+  L.ctr2 = take(bc * (k + 1) * 16);
+  L.kp_ctr = L.ctr2 + bc * 16;
+  L.mi = take(bc * (k + 1) * 4);
+  L.ni = take(bc * (k + 1) * 4);
   L.labels = take(bn);
   L.sel_pos = take(bn * 4);
   L.sel_base = take(bc * 4);
-  L.pts_ctr = take(bn * 16);
-  L.pts_kp = take(bn * k * 16);
+  // one vote buffer: centre votes [0, bn) then keypoint votes [bn, bn + bn*k)
+  L.pts_ctr = take(bn * (k + 1) * 16);
+  L.pts_kp = L.pts_ctr + bn * 16;
   L.present = take(bc);
-  L.ms = take(meanshift_ws_bytes(static_cast<int>(bn * k), static_cast<int>(bc * k), max_iter));
+  L.ms = take(meanshift_ws_bytes(static_cast<int>(bn * (k + 1)), static_cast<int>(bc * (k + 1)), max_iter));
   L.total = off;
   return L;
 }
@@ -487,7 +492,7 @@ extern "C" int pvn3d_best_fit_transform_batch(const float *a, const float *b, co
 
 extern "C" size_t pvn3d_frame_poses_workspace_bytes(int b, int n, int k, int n_cls, int max_iter) {
   if (b <= 0 || n <= 0 || k <= 0 || n_cls <= 0 || max_iter < 0 || max_iter > 4094) return 0;
-  if (static_cast<long long>(b) * n * k > 0x7fffffffll) return 0;
+  if (static_cast<long long>(b) * n * (k + 1) > 0x7fffffffll) return 0;
   return pose_layout(b, n, k, n_cls, max_iter).total;
 }
 
@@ -504,7 +509,7 @@ extern "C" int pvn3d_frame_poses_batch(const float *pcld, const int *mask, const
   if (use_ctr_clus_flter && !cls_radius) return PVN3D_ERR_INVALID_ARG;
   if (b == 0) return PVN3D_OK;
   if (n_cls > kMaxCls || k > kMaxKabschPts || b > 65535) return PVN3D_ERR_UNSUPPORTED;
-  if (static_cast<long long>(b) * n * k > 0x7fffffffll) return PVN3D_ERR_UNSUPPORTED;
+  if (static_cast<long long>(b) * n * (k + 1) > 0x7fffffffll) return PVN3D_ERR_UNSUPPORTED;
   if (max_iter < 0 || max_iter > 4094) return PVN3D_ERR_UNSUPPORTED;
   const PoseLayout L = pose_layout(b, n, k, n_cls, max_iter);
   if (workspace_bytes < L.total) return PVN3D_ERR_WORKSPACE;
@@ -535,7 +540,7 @@ extern "C" int pvn3d_frame_poses_batch(const float *pcld, const int *mask, const
                                                  F4(L.pts_ctr));
     if ((rc = check_launch("build_ctr_votes_kernel")) != PVN3D_OK) return rc;
     rc = meanshift_launch(F4(L.pts_ctr), I(L.fs_ctr), I(L.fc_ctr), bc, b * n, bandwidth, max_iter,
-                          ms_flags, F4(L.ctr1), nullptr, I(L.mi), I(L.ni), ws + L.ms, st);
+                          ms_flags, F4(L.ctr1), nullptr, I(L.mi), I(L.ni), ws + L.ms, st, false);
     if (rc != PVN3D_OK) return rc;
     relabel_kernel<<<gpts, 256, 0, st>>>(pcld, ctr_of, mask, F4(L.ctr1), I(L.cls_off), cls_radius,
                                          n, n_cls, nm);
@@ -559,22 +564,26 @@ extern "C" int pvn3d_frame_poses_batch(const float *pcld, const int *mask, const
   build_ctr_votes_kernel<<<gpts, 256, 0, st>>>(pcld, ctr_of, perm_v, off_v, n, n_cls,
                                                F4(L.pts_ctr));
   if ((rc = check_launch("build_ctr_votes_kernel(2)")) != PVN3D_OK) return rc;
+  // exact pass of the centre fits only: the inlier labels depend on the INPUT votes alone
+  // (meanshift_pytorch.py:46-50), so the keypoint vote sets can be formed before any iteration runs
   uint8_t *labels = reinterpret_cast<uint8_t *>(ws + L.labels);
   rc = meanshift_launch(F4(L.pts_ctr), I(L.fs_ctr), I(L.fc_ctr), bc, b * n, bandwidth, max_iter,
-                        ms_flags, F4(L.ctr2), labels, I(L.mi), I(L.ni), ws + L.ms, st);
+                        ms_flags, F4(L.ctr2), labels, I(L.mi), I(L.ni), ws + L.ms, st, true);
   if (rc != PVN3D_OK) return rc;
 
   // keypoint votes of the centre-cluster inliers, one fit per (class, keypoint)     (:91-97)
   kp_layout_kernel<<<b, kCompactThreads, 0, st>>>(use_ctr_clus_flter ? labels : nullptr, off_v, n,
-                                                  n_cls, k, I(L.sel_pos), I(L.sel_base),
+                                                  n_cls, k, b * n, I(L.sel_pos), I(L.sel_base),
                                                   I(L.fs_kp), I(L.fc_kp));
   if ((rc = check_launch("kp_layout_kernel")) != PVN3D_OK) return rc;
   build_kp_votes_kernel<<<dim3(ceil_div(n, 256), k, b), 256, 0, st>>>(
       pcld, kp_of, perm_v, mask_v, off_v, I(L.sel_pos), I(L.sel_base), I(L.fs_kp), n, n_cls, k,
-      F4(L.pts_kp));
+      F4(L.pts_ctr));
   if ((rc = check_launch("build_kp_votes_kernel")) != PVN3D_OK) return rc;
-  rc = meanshift_launch(F4(L.pts_kp), I(L.fs_kp), I(L.fc_kp), bc * k, b * n * k, bandwidth,
-                        max_iter, ms_flags, F4(L.kp_ctr), nullptr, I(L.mi), I(L.ni), ws + L.ms, st);
+  // ONE mean-shift launch for the centre fit and the K keypoint fits of every class of every frame
+  rc = meanshift_launch(F4(L.pts_ctr), I(L.fs_ctr), I(L.fc_ctr), bc * (k + 1), b * n * (k + 1),
+                        bandwidth, max_iter, ms_flags, F4(L.ctr2), nullptr, I(L.mi), I(L.ni),
+                        ws + L.ms, st, false);
   if (rc != PVN3D_OK) return rc;
 
   // least-squares pose per class                                                   (:99-107)

@@ -21,6 +21,9 @@ KEYS = ["launch__grid_size", "launch__block_size", "launch__registers_per_thread
         "smsp__inst_executed.sum", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lts__t_bytes.sum",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_subpipe_tmem_cycles_active.avg.pct_of_peak_sustained_active",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
 
 
@@ -73,4 +76,5 @@ if __name__ == "__main__":
     launches(tag)
     full(tag, "qg")
     full(tag, "ms")
+    full(tag, "mlp")
     print(os.listdir(OUT))
