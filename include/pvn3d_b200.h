@@ -115,10 +115,18 @@ int pvn3d_transpose_nc_to_cn(const float *src_bnc, int b, int n, int c, float *d
  *   descriptors (ldf >= C; C may be 0 -> feat_pm NULL)
  *   -> idx[B,M,S] (may be NULL), out[B,3+C,M,S]   == QueryAndGroup(radius,S,use_xyz=True).forward
  * idx bit-exact with pvn3d_ball_query; out bit-exact with the composed reference ops.
- * Supported: 1 <= S <= 256 (larger S: compose pvn3d_ball_query + pvn3d_group_points). */
+ * Supported: S <= 256 per scale (larger S: compose pvn3d_ball_query + pvn3d_group_points). */
 int pvn3d_query_and_group(const float *xyz, const float *new_xyz, const float *feat_pm, int ldf,
                           int b, int n, int m, int c, float radius, int nsample, int *idx,
                           float *out, pvn3d_stream_t stream);
+
+/* The two scales of one multi-scale-grouping level in ONE launch (same centres, same cloud: every
+ * squared distance is evaluated once and compared with both radii).  Per scale either output may be
+ * NULL: out NULL = ball query only (idx), idx NULL = grouped tensor only. */
+int pvn3d_query_and_group2(const float *xyz, const float *new_xyz, const float *feat_pm, int ldf,
+                           int b, int n, int m, int c, float radius0, int nsample0, int *idx0,
+                           float *out0, float radius1, int nsample1, int *idx1, float *out1,
+                           pvn3d_stream_t stream);
 
 /* three_nn + (1/(sqrt(d2)+1e-8) normalised) weights + three_interpolate, point-major features:
  *   unknown[B,n,3], known[B,m,3], known_feat_pm[B,m,C] -> out_pm[B,n,ldo] columns [col0,col0+C)

@@ -241,6 +241,34 @@ def query_and_group(xyz, new_xyz, feat_pm, radius: float, nsample: int, ldf=None
     return out, idx
 
 
+def query_and_group2(xyz, new_xyz, feat_pm, radii, nsamples, ldf=None, c=None, want_idx=True, want_out=True):
+    """Both scales of an MSG level in one launch.  Returns ([out0, out1], [idx0, idx1]) (None where not wanted)."""
+    for t, nm in ((xyz, "xyz"), (new_xyz, "new_xyz")):
+        _chk_contig(t, nm); _chk_float(t, nm)
+    _need_cuda(xyz)
+    b, n = xyz.size(0), xyz.size(1)
+    m = new_xyz.size(1)
+    if feat_pm is not None and want_out:
+        _chk_contig(feat_pm, "feat_pm"); _chk_float(feat_pm, "feat_pm")
+        ldf = feat_pm.size(-1) if ldf is None else int(ldf)
+        c = ldf if c is None else int(c)
+    else:
+        ldf, c = (0, 0) if ldf is None else (int(ldf), int(c or 0))
+    outs = [torch.empty((b, 3 + c, m, int(ns)), dtype=torch.float32, device=xyz.device) if want_out else None
+            for ns in nsamples]
+    idxs = [torch.empty((b, m, int(ns)), dtype=torch.int32, device=xyz.device) if want_idx else None for ns in nsamples]
+    _call("pvn3d_query_and_group2", xyz.device, ptr(xyz), ptr(new_xyz), ptr(feat_pm) if want_out else 0, ldf, b, n, m, c,
+          float(radii[0]), int(nsamples[0]), ptr(idxs[0]), ptr(outs[0]),
+          float(radii[1]), int(nsamples[1]), ptr(idxs[1]), ptr(outs[1]))
+    return outs, idxs
+
+
+def ball_query2(new_xyz, xyz, radii, nsamples):
+    """ball_query for the two radii of an MSG level in one pass over the cloud -> (idx0, idx1)."""
+    _, idxs = query_and_group2(xyz, new_xyz, None, radii, nsamples, want_idx=True, want_out=False)
+    return idxs[0], idxs[1]
+
+
 def three_nn_interpolate(unknown, known, known_feat_pm, out_pm=None, col0=0, want_nn=False):
     """three_nn + inverse-distance weights + three_interpolate on point-major features.
     unknown [B,n,3], known [B,m,3], known_feat_pm [B,m,C] -> out_pm [B,n,ldo] (columns col0..col0+C)."""

@@ -169,8 +169,8 @@ class FusedPointnet2MSG:
             new_xyz = torch.gather(x, 1, fidx.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
             out_l = torch.empty((b, npoint, self.sa_out[li]), dtype=torch.float32, device=self.dev)
             col = 0
-            for (r, ns, layers) in zip(radii, nsamples, self.sa[li]):
-                idx = _ext.ball_query(new_xyz, x, r, ns)
+            idxs = _ext.ball_query2(new_xyz, x, radii, nsamples)    # one pass over the cloud for both radii
+            for (idx, ns, layers) in zip(idxs, nsamples, self.sa[li]):
                 h = mlp_sa_first(x, new_xyz, fptr, ldf, c_feat, idx, layers[0])
                 for mid in layers[1:-1]:
                     h = mlp_dense(h, mid)

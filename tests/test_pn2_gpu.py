@@ -207,3 +207,23 @@ def test_contract_errors(cuda_dev):
         _ext.gather_points(torch.zeros(1, 3, 8, device=cuda_dev), torch.zeros(1, 2, device=cuda_dev))
     with pytest.raises(RuntimeError, match="must be a float tensor"):
         _ext.ball_query(torch.zeros(1, 2, 3, device=cuda_dev).double(), torch.zeros(1, 8, 3, device=cuda_dev), 0.1, 4)
+
+
+def test_query_and_group2_both_radii_in_one_launch(cuda_dev, clouds):
+    """The two scales of every MSG level from ONE launch == two oracle QueryAndGroup calls, bit for bit;
+    idx-only form (ball_query2) == ball_query twice."""
+    _, levels = clouds
+    rng = np.random.default_rng(12)
+    for li, c in [(0, 6), (1, 96), (2, 256), (3, 512), (1, 40)]:
+        xyz, new = levels[li], levels[li + 1]
+        n = xyz.shape[1]
+        feats = rng.normal(size=(2, c, n)).astype(np.float32)
+        radii, nss = SA_LEVELS[li][2], SA_LEVELS[li][3]
+        feat_pm = _ext.transpose_cn_to_nc(t(feats, cuda_dev))
+        outs, idxs = _ext.query_and_group2(t(xyz, cuda_dev), t(new, cuda_dev), feat_pm, radii, nss)
+        i0, i1 = _ext.ball_query2(t(new, cuda_dev), t(xyz, cuda_dev), radii, nss)
+        for s in range(2):
+            want, widx = pn2.query_and_group(xyz, new, feats, float(np.float32(radii[s])), nss[s])
+            assert np.array_equal(idxs[s].cpu().numpy(), widx), (li, c, s)
+            assert np.array_equal(outs[s].cpu().numpy(), want), (li, c, s)
+            assert np.array_equal((i0, i1)[s].cpu().numpy(), widx), (li, c, s)
