@@ -9,16 +9,19 @@
 // every squared distance is computed once and compared against both radii).
 //
 // Per CTA (8 warps, CW centres per warp):
-//   phase 1  the cloud's xyz streams through shared memory in 24 KB tiles (1-D bulk copy by the TMA
-//            engine, mbarrier completion); a warp ballots 32 points per step against its CW centres,
-//            hits are appended in index order (the reference's first-nsample rule by construction);
-//            the common no-hit step costs 3 LDS + ~11 instructions per centre for both radii.
+//   phase 1  the cloud's xyz streams through shared memory in double-buffered 12 KB tiles (1-D bulk
+//            copies by the TMA engine, mbarrier completion; the copy of tile i+1 overlaps the scan of
+//            tile i); a warp ballots 32 points per step against its CW centres, hits are appended in
+//            index order (the reference's first-nsample rule by construction).  Every 128-point block
+//            of a tile carries a bounding box; blocks out of reach of all of the warp's open balls
+//            are skipped -- exact pruning that costs nothing on shuffled clouds and removes most of
+//            the scan on raster-ordered ones (the reference's samplers keep raster order).
 //   phase 2  descriptors are read POINT-MAJOR (feat_pm[B,N,ldf]).  A warp owns 32 consecutive slots:
-//            it pulls 64 channels of two neighbours per LDG.128 (each half-warp one fully used
-//            256-byte run), parks them in a private shared-memory tile, and writes the channel-major
-//            output as 16-byte stores -- 8 lanes cover one 128-byte line of a channel row, a warp
-//            instruction four rows -- after a 4x4 register transpose.  Every output byte is written
-//            once, every gathered sector is fully used, ~0.015 instructions per byte.
+//            cp.async pulls 32 channels of four neighbours per instruction (8 lanes = one fully used
+//            128-byte run) into one of two private shared-memory tiles while the previous tile is
+//            written out as 16-byte stores -- 8 lanes cover one 128-byte line of a channel row, a
+//            warp instruction four rows -- after a 4x4 register transpose.  Every output byte is
+//            written once, every gathered sector is fully used.
 // Algorithmic HBM bytes per launch and scale:
 //   B * [ 12 N + 12 M + 4 C N  (reads)  +  4 M S + 4 (3+C) M S  (writes) ].
 #include "common.cuh"
@@ -28,9 +31,13 @@ namespace {
 
 constexpr int kQgThreads = 256;
 constexpr int kQgWarps = 8;
-constexpr int kQgTile = 2048;      // xyz points per shared-memory tile (24 KB)
+constexpr int kQgTile = 1024;      // xyz points per shared-memory tile (12 KB), double buffered
+constexpr int kQgBlock = 128;      // points per bounding-box block of a tile (8 blocks per tile)
 constexpr int kQgMaxSlots = 2048;  // slots (centres x nsample, both scales) per CTA
-constexpr int kQgTrStride = 68;    // floats per row of the per-warp [32 slots][64 channels] tile
+constexpr int kQgTrStride = 36;    // floats per row of a per-warp [32 slots][32 channels] tile
+constexpr int kQgTrFloats = 32 * kQgTrStride;  // one tile; every warp owns two (double buffering)
+static_assert(kQgTile / kQgBlock == kQgWarps, "one bounding-box block per warp");
+static_assert(2 * kQgTrFloats >= 32 * 33, "scalar fallback transposes through the same buffer");
 
 struct QgScale {
   float radius;
@@ -45,9 +52,9 @@ struct QgArgs {
 };
 
 struct QgSmem {
-  static constexpr size_t tile_bytes = kQgTile * 3 * sizeof(float);                        // 24576
+  static constexpr size_t tile_bytes = 2 * kQgTile * 3 * sizeof(float);                    // 24576
   static constexpr size_t rows_bytes = kQgMaxSlots * sizeof(int);                          // 8192
-  static constexpr size_t tr_bytes = kQgWarps * 32 * kQgTrStride * sizeof(float);          // 69632
+  static constexpr size_t tr_bytes = kQgWarps * 2 * kQgTrFloats * sizeof(float);           // 73728
   static constexpr size_t total = tile_bytes + rows_bytes + tr_bytes;
 };
 
@@ -57,6 +64,15 @@ __device__ __forceinline__ void qg_append(unsigned hits, int &cnt, int &first, i
   const int slot = cnt + __popc(hits & lanemask_lt());
   if (((hits >> lane) & 1u) && slot < ns) row[slot] = kbase + static_cast<int>(lane);
   cnt += __popc(hits);
+}
+
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 // write one scale's slots of this CTA: xyz difference channels + descriptor channels
@@ -87,75 +103,89 @@ __device__ __forceinline__ void qg_write_scale(const QgArgs &a, const QgScale &s
   const float *feat_b = a.feat + static_cast<size_t>(b) * a.n * a.ldf;
   float *out_f = out_b + 3 * plane;
   const bool vec = (c % 4 == 0) && (a.ldf % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.feat) & 15u) == 0) &&
-                   (plane % 4 == 0) && (slot_base % 4 == 0) &&
+                   (plane % 4 == 0) && (slot_base % 4 == 0) && (ns % 4 == 0) &&
                    ((reinterpret_cast<uintptr_t>(sc.out) & 15u) == 0);
-  float *tr = s_tr + warp * (32 * kQgTrStride);
+  float *tr = s_tr + warp * (2 * kQgTrFloats);
   const int ngroups = (nslots + 31) / 32;
-  for (int g = warp; g < ngroups; g += kQgWarps) {  // warp-uniform
-    const int g0 = g * 32;
-    const int glive = min(32, nslots - g0);
-    if (vec) {
-      const int half = lane >> 4, chunk = lane & 15;  // gather: two neighbours per instruction
-      const int m8 = lane >> 2, k4 = lane & 3;        // output: slots 4*m8.., channel quad k4
-      for (int c0 = 0; c0 < c; c0 += 64) {
-        const int quads = min(16, (c - c0) / 4);
-        __syncwarp();
-#pragma unroll 4
-        for (int i = 0; i < 16; ++i) {
-          const int q = 2 * i + half;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (q < glive && chunk < quads)
-            v = __ldg(reinterpret_cast<const float4 *>(feat_b + static_cast<size_t>(rows[g0 + q]) * a.ldf +
-                                                       c0 + 4 * chunk));
-          *reinterpret_cast<float4 *>(tr + q * kQgTrStride + 4 * chunk) = v;
-        }
-        __syncwarp();
-        if (4 * m8 < glive) {
+  if (vec) {
+    // Work items of this warp: (group g of 32 slots, chunk of 32 channels).  The neighbour rows of
+    // item i+1 are fetched with cp.async (16 B per lane, 8 lanes = one 128-byte run of a row, four
+    // rows per instruction) into the other buffer while item i is transposed and stored.
+    const int nchunks = (c + 31) / 32;
+    const int my_groups = (ngroups > static_cast<int>(warp)) ? (ngroups - static_cast<int>(warp) + kQgWarps - 1) / kQgWarps : 0;
+    const int items = my_groups * nchunks;
+    const int sub = lane >> 3, chunk = lane & 7;  // gather: neighbour sub-row, 16-byte chunk
+    const int m8 = lane >> 2, k4 = lane & 3;      // store: slots 4*m8.., channel quad
+    auto issue = [&](int item, float *buf) {
+      const int g0 = (static_cast<int>(warp) + (item / nchunks) * kQgWarps) * 32;
+      const int c0 = (item % nchunks) * 32;
+      const int glive = min(32, nslots - g0);
+      const int quads = min(8, (c - c0) / 4);
+      if (chunk < quads) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int quad = 4 * j + k4;
-            if (quad < quads) {
-              const float4 v0 = *reinterpret_cast<const float4 *>(tr + (4 * m8 + 0) * kQgTrStride + 4 * quad);
-              const float4 v1 = *reinterpret_cast<const float4 *>(tr + (4 * m8 + 1) * kQgTrStride + 4 * quad);
-              const float4 v2 = *reinterpret_cast<const float4 *>(tr + (4 * m8 + 2) * kQgTrStride + 4 * quad);
-              const float4 v3 = *reinterpret_cast<const float4 *>(tr + (4 * m8 + 3) * kQgTrStride + 4 * quad);
-              float *dst = out_f + static_cast<size_t>(c0 + 4 * quad) * plane + g0 + 4 * m8;
-              if (4 * m8 + 4 <= glive) {
-                stg_stream4(dst + 0 * plane, make_float4(v0.x, v1.x, v2.x, v3.x));
-                stg_stream4(dst + 1 * plane, make_float4(v0.y, v1.y, v2.y, v3.y));
-                stg_stream4(dst + 2 * plane, make_float4(v0.z, v1.z, v2.z, v3.z));
-                stg_stream4(dst + 3 * plane, make_float4(v0.w, v1.w, v2.w, v3.w));
-              } else {  // ragged last quad of slots
-                const float e0[4] = {v0.x, v0.y, v0.z, v0.w}, e1[4] = {v1.x, v1.y, v1.z, v1.w},
-                            e2[4] = {v2.x, v2.y, v2.z, v2.w};
-                for (int e = 0; e < 4; ++e) {
-                  dst[e * plane] = e0[e];
-                  if (4 * m8 + 1 < glive) dst[e * plane + 1] = e1[e];
-                  if (4 * m8 + 2 < glive) dst[e * plane + 2] = e2[e];
-                }
-              }
-            }
+        for (int i = 0; i < 8; ++i) {
+          const int q = 4 * i + sub;
+          if (q < glive)
+            cp_async16(buf + q * kQgTrStride + 4 * chunk,
+                       feat_b + static_cast<size_t>(rows[g0 + q]) * a.ldf + c0 + 4 * chunk);
+        }
+      }
+      cp_async_commit();
+    };
+    if (items > 0) issue(0, tr);
+    for (int item = 0; item < items; ++item) {
+      float *buf = tr + (item & 1) * kQgTrFloats;
+      if (item + 1 < items) {
+        issue(item + 1, tr + ((item + 1) & 1) * kQgTrFloats);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncwarp();
+      const int g0 = (static_cast<int>(warp) + (item / nchunks) * kQgWarps) * 32;
+      const int c0 = (item % nchunks) * 32;
+      const int glive = min(32, nslots - g0);  // multiple of 4 (ns % 4 == 0)
+      const int quads = min(8, (c - c0) / 4);
+      if (4 * m8 < glive) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int quad = 4 * j + k4;
+          if (quad < quads) {
+            const float4 v0 = *reinterpret_cast<const float4 *>(buf + (4 * m8 + 0) * kQgTrStride + 4 * quad);
+            const float4 v1 = *reinterpret_cast<const float4 *>(buf + (4 * m8 + 1) * kQgTrStride + 4 * quad);
+            const float4 v2 = *reinterpret_cast<const float4 *>(buf + (4 * m8 + 2) * kQgTrStride + 4 * quad);
+            const float4 v3 = *reinterpret_cast<const float4 *>(buf + (4 * m8 + 3) * kQgTrStride + 4 * quad);
+            float *dst = out_f + static_cast<size_t>(c0 + 4 * quad) * plane + g0 + 4 * m8;
+            stg_stream4(dst + 0 * plane, make_float4(v0.x, v1.x, v2.x, v3.x));
+            stg_stream4(dst + 1 * plane, make_float4(v0.y, v1.y, v2.y, v3.y));
+            stg_stream4(dst + 2 * plane, make_float4(v0.z, v1.z, v2.z, v3.z));
+            stg_stream4(dst + 3 * plane, make_float4(v0.w, v1.w, v2.w, v3.w));
           }
         }
       }
-    } else {
-      // generic rows (odd channel counts / unaligned strides): scalar 32x32 transposes
-      const int p = (static_cast<int>(lane) < glive) ? rows[g0 + lane] : 0;
-      for (int c0 = 0; c0 < c; c0 += 32) {
-        const int cw = min(32, c - c0);
-        __syncwarp();
-        for (int q = 0; q < 32; ++q) {
-          const int pq = __shfl_sync(0xffffffffu, p, q);
-          float v = 0.f;
-          if (static_cast<int>(lane) < cw && q < glive)
-            v = __ldg(feat_b + static_cast<size_t>(pq) * a.ldf + c0 + lane);
-          tr[lane * 33 + q] = v;
-        }
-        __syncwarp();
-        if (static_cast<int>(lane) < glive) {
-          float *dst = out_f + static_cast<size_t>(c0) * plane + g0 + lane;
-          for (int cc = 0; cc < cw; ++cc) stg_stream(dst + cc * plane, tr[cc * 33 + lane]);
-        }
+      __syncwarp();  // buffer (item & 1) is refilled two items later
+    }
+    return;
+  }
+  // generic rows (odd channel counts / unaligned strides): scalar 32x32 transposes
+  for (int g = warp; g < ngroups; g += kQgWarps) {  // warp-uniform
+    const int g0 = g * 32;
+    const int glive = min(32, nslots - g0);
+    const int p = (static_cast<int>(lane) < glive) ? rows[g0 + lane] : 0;
+    for (int c0 = 0; c0 < c; c0 += 32) {
+      const int cw = min(32, c - c0);
+      __syncwarp();
+      for (int q = 0; q < 32; ++q) {
+        const int pq = __shfl_sync(0xffffffffu, p, q);
+        float v = 0.f;
+        if (static_cast<int>(lane) < cw && q < glive)
+          v = __ldg(feat_b + static_cast<size_t>(pq) * a.ldf + c0 + lane);
+        tr[lane * 33 + q] = v;
+      }
+      __syncwarp();
+      if (static_cast<int>(lane) < glive) {
+        float *dst = out_f + static_cast<size_t>(c0) * plane + g0 + lane;
+        for (int cc = 0; cc < cw; ++cc) stg_stream(dst + cc * plane, tr[cc * 33 + lane]);
       }
     }
   }
@@ -164,10 +194,11 @@ __device__ __forceinline__ void qg_write_scale(const QgArgs &a, const QgScale &s
 template <int CW, bool DUAL>
 __global__ void __launch_bounds__(kQgThreads, 2) query_group_kernel(QgArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float *s_tile = reinterpret_cast<float *>(smem_raw);
+  float *s_tile = reinterpret_cast<float *>(smem_raw);  // two tiles of kQgTile points
   int *s_rows = reinterpret_cast<int *>(smem_raw + QgSmem::tile_bytes);
   float *s_tr = reinterpret_cast<float *>(smem_raw + QgSmem::tile_bytes + QgSmem::rows_bytes);
-  __shared__ uint64_t s_bar;
+  __shared__ uint64_t s_bar[2];
+  __shared__ float s_bbox[kQgTile / kQgBlock][6];  // per 128-point block of the current tile
 
   constexpr int TJ = kQgWarps * CW;
   const int b = blockIdx.y;
@@ -178,11 +209,15 @@ __global__ void __launch_bounds__(kQgThreads, 2) query_group_kernel(QgArgs a) {
   const int nsa = a.s[0].ns, nsb = DUAL ? a.s[1].ns : 0;
   const float r2a = __fmul_rn(a.s[0].radius, a.s[0].radius);  // ball_query_gpu.cu:22
   const float r2b = DUAL ? __fmul_rn(a.s[1].radius, a.s[1].radius) : 0.f;
-  int *rows_a = s_rows;                  // [TJ][nsa]
-  int *rows_b = s_rows + TJ * nsa;       // [TJ][nsb]
+  // a block can be skipped when even its bounding box is out of reach of the larger radius; the bound
+  // is inflated so that fp32 rounding of the box distance can never hide a true hit
+  const float r2skip = fmaxf(r2a, r2b) * 1.0001f + 1e-12f;
+  int *rows_a = s_rows;             // [TJ][nsa]
+  int *rows_b = s_rows + TJ * nsa;  // [TJ][nsb]
 
   if (threadIdx.x == 0) {
-    mbar_init(&s_bar, 1);
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
     mbar_fence_init();
   }
   // ---------------- phase 1: warp w scans for centres w*CW .. w*CW+CW-1 of the CTA ----------------
@@ -202,44 +237,114 @@ __global__ void __launch_bounds__(kQgThreads, 2) query_group_kernel(QgArgs a) {
   }
   __syncthreads();
 
-  unsigned phase = 0;
+  // tile i lives in buffer i&1; the copy of tile i+1 is in flight while tile i is scanned
+  const int ntiles = (a.n + kQgTile - 1) / kQgTile;
+  const bool bulk = ((reinterpret_cast<uintptr_t>(cloud) & 15u) == 0);  // tile offsets are 16-B multiples
+  auto tile_count = [&](int i) { return min(kQgTile, a.n - i * kQgTile); };
+  auto issue_tile = [&](int i) {  // called by thread 0 (bulk) or by everyone (fallback)
+    const int cnt = tile_count(i);
+    const unsigned bytes = static_cast<unsigned>(cnt) * 12u;
+    float *dst = s_tile + (i & 1) * (kQgTile * 3);
+    const float *src = cloud + static_cast<size_t>(i) * kQgTile * 3;
+    if (bulk && (bytes & 15u) == 0u) {
+      if (threadIdx.x == 0) {
+        mbar_expect_tx(&s_bar[i & 1], bytes);
+        bulk_g2s(dst, src, bytes, &s_bar[i & 1]);
+      }
+    } else {
+      for (int e = threadIdx.x; e < cnt * 3; e += kQgThreads) dst[e] = __ldg(src + e);
+    }
+  };
+  auto wait_tile = [&](int i, unsigned (&ph)[2]) {
+    const unsigned bytes = static_cast<unsigned>(tile_count(i)) * 12u;
+    if (bulk && (bytes & 15u) == 0u) {
+      mbar_wait(&s_bar[i & 1], ph[i & 1]);
+      ph[i & 1] ^= 1u;
+    }
+  };
+  unsigned ph[2] = {0u, 0u};
   bool warp_open = static_cast<int>(warp) * CW < live_centres;
-  for (int base = 0; base < a.n; base += kQgTile) {
-    const int count = min(kQgTile, a.n - base);
-    stage_xyz_tile(s_tile, cloud, base, count, &s_bar, phase, true);
+  issue_tile(0);
+  for (int ti = 0; ti < ntiles; ++ti) {
+    const int base = ti * kQgTile;
+    const int count = tile_count(ti);
+    const float *tile = s_tile + (ti & 1) * (kQgTile * 3);
+    if (ti + 1 < ntiles) issue_tile(ti + 1);  // buffer (ti+1)&1 was released by the barrier ending tile ti-1
+    wait_tile(ti, ph);
+    __syncthreads();  // fallback path: plain stores of tile ti visible (also orders s_bbox reuse)
+    // bounding box of every 128-point block: warp w takes block w
+    {
+      const int blk0 = static_cast<int>(warp) * kQgBlock;
+      float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+      for (int k = blk0 + static_cast<int>(lane); k < min(blk0 + kQgBlock, count); k += 32) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          const float v = tile[k * 3 + d];
+          lo[d] = fminf(lo[d], v);
+          hi[d] = fmaxf(hi[d], v);
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+          hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+        }
+      }
+      if (lane < 3) {
+        s_bbox[warp][lane] = lo[lane];
+        s_bbox[warp][3 + lane] = hi[lane];
+      }
+    }
+    __syncthreads();
     if (warp_open) {
-      for (int off = 0; off < count; off += 32) {
-        const int kk = off + static_cast<int>(lane);
-        const bool in = kk < count;
-        const float x = in ? s_tile[kk * 3 + 0] : 0.f;
-        const float y = in ? s_tile[kk * 3 + 1] : 0.f;
-        const float z = in ? s_tile[kk * 3 + 2] : 0.f;
+      for (int blk = 0; blk * kQgBlock < count; ++blk) {
+        // distance from each centre to the block's box (0 inside); NaN coordinates fail the skip test
+        bool reach = false;
 #pragma unroll
         for (int q = 0; q < CW; ++q) {
-          const float d2 = ref_sqdist(cx[q] - x, cy[q] - y, cz[q] - z);
-          const unsigned ha = __ballot_sync(0xffffffffu, in && d2 < r2a);
-          const unsigned hb = DUAL ? __ballot_sync(0xffffffffu, in && d2 < r2b) : 0u;
-          if (ha | hb) {  // rare: a step with a neighbour in it
-            const int lc = static_cast<int>(warp) * CW + q;
-            if (ha && cnta[q] < nsa) qg_append(ha, cnta[q], firsta[q], nsa, rows_a + lc * nsa, base + off, lane);
-            if (DUAL && hb && cntb[q] < nsb)
-              qg_append(hb, cntb[q], firstb[q], nsb, rows_b + lc * nsb, base + off, lane);
-          }
+          const bool open_q = (cnta[q] < nsa) || (DUAL && cntb[q] < nsb);
+          const float ex = fmaxf(fmaxf(s_bbox[blk][0] - cx[q], cx[q] - s_bbox[blk][3]), 0.f);
+          const float ey = fmaxf(fmaxf(s_bbox[blk][1] - cy[q], cy[q] - s_bbox[blk][4]), 0.f);
+          const float ez = fmaxf(fmaxf(s_bbox[blk][2] - cz[q], cz[q] - s_bbox[blk][5]), 0.f);
+          reach |= open_q && !(ex * ex + ey * ey + ez * ez > r2skip);
         }
-        if ((off & 255) == 224) {  // every 8 steps: stop once every ball of this warp is full
-          bool open = false;
+        if (!reach) continue;  // warp-uniform
+        const int off_end = min((blk + 1) * kQgBlock, count);
+        for (int off = blk * kQgBlock; off < off_end; off += 32) {
+          const int kk = off + static_cast<int>(lane);
+          const bool in = kk < count;
+          const float x = in ? tile[kk * 3 + 0] : 0.f;
+          const float y = in ? tile[kk * 3 + 1] : 0.f;
+          const float z = in ? tile[kk * 3 + 2] : 0.f;
 #pragma unroll
-          for (int q = 0; q < CW; ++q) open |= (cnta[q] < nsa) || (DUAL && cntb[q] < nsb);
-          if (!open) {
-            warp_open = false;
-            break;
+          for (int q = 0; q < CW; ++q) {
+            const float d2 = ref_sqdist(cx[q] - x, cy[q] - y, cz[q] - z);
+            const unsigned ha = __ballot_sync(0xffffffffu, in && d2 < r2a);
+            const unsigned hb = DUAL ? __ballot_sync(0xffffffffu, in && d2 < r2b) : 0u;
+            if (ha | hb) {  // rare: a step with a neighbour in it
+              const int lc = static_cast<int>(warp) * CW + q;
+              if (ha && cnta[q] < nsa)
+                qg_append(ha, cnta[q], firsta[q], nsa, rows_a + lc * nsa, base + off, lane);
+              if (DUAL && hb && cntb[q] < nsb)
+                qg_append(hb, cntb[q], firstb[q], nsb, rows_b + lc * nsb, base + off, lane);
+            }
           }
         }
       }
+      bool open = false;
+#pragma unroll
+      for (int q = 0; q < CW; ++q) open |= (cnta[q] < nsa) || (DUAL && cntb[q] < nsb);
+      warp_open = open;
     }
-    // barrier: tile consumed by every warp before it is overwritten; the OR tells all threads the
+    // barrier: tile consumed by every warp before its buffer is refilled; the OR tells all threads the
     // same thing -- whether any ball of this CTA is still unfilled
-    if (!__syncthreads_or(warp_open ? 1 : 0)) break;
+    if (!__syncthreads_or(warp_open ? 1 : 0)) {
+      // a copy of tile ti+1 may still be in flight: drain it before the buffer is reused / the CTA exits
+      if (ti + 1 < ntiles) wait_tile(ti + 1, ph);
+      break;
+    }
   }
   // pad the rows: slots >= cnt repeat the first hit (0 for an empty ball: torch::zeros, ball_query.cpp:19)
   __syncwarp();
