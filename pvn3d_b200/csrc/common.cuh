@@ -44,6 +44,8 @@ struct PerDeviceOnce {
   }
 };
 
+int keep_async_pool_warm();  // call before cudaMallocAsync scratch allocations
+
 static inline cudaStream_t as_stream(pvn3d_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

@@ -205,6 +205,8 @@ extern "C" int pvn3d_furthest_point_sampling(const float *xyz, int b, int n, int
   if (ppt <= 24) return launch_regs<24>(xyz, b, n, m, log2_bs, idx, st);
 
   // large clouds: stream-ordered scratch for the running min-distances
+  int rc0 = keep_async_pool_warm();
+  if (rc0 != PVN3D_OK) return rc0;
   float *temp = nullptr;
   PVN3D_CUDA_TRY(cudaMallocAsync(&temp, static_cast<size_t>(b) * n * sizeof(float), st),
                  "fps scratch alloc");

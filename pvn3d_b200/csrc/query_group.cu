@@ -9,13 +9,14 @@
 // every squared distance is computed once and compared against both radii).
 //
 // Per CTA (8 warps, CW centres per warp):
-//   phase 1  the cloud's xyz streams through shared memory in double-buffered 12 KB tiles (1-D bulk
-//            copies by the TMA engine, mbarrier completion; the copy of tile i+1 overlaps the scan of
-//            tile i); a warp ballots 32 points per step against its CW centres, hits are appended in
-//            index order (the reference's first-nsample rule by construction).  Every 128-point block
-//            of a tile carries a bounding box; blocks out of reach of all of the warp's open balls
-//            are skipped -- exact pruning that costs nothing on shuffled clouds and removes most of
-//            the scan on raster-ordered ones (the reference's samplers keep raster order).
+//   phase 1  every 128-point block of the cloud gets a bounding box (and every 8 blocks a super box) in
+//            shared memory; then each warp walks the cloud ON ITS OWN -- no tile staging, no CTA
+//            barriers -- balloting 32 points per step against its CW centres (hits are appended in
+//            index order: the reference's first-nsample rule by construction) and skipping every
+//            block whose box is out of reach of the box of its centres.  Exact pruning: free on
+//            shuffled clouds, removes ~90 % of the scan on raster-ordered ones (the reference's
+//            samplers keep raster order).  The cloud is read through L1/L2 (384 contiguous bytes per
+//            step); the TMA-staged variant of the scan lives on in pn2_ops.cu:ball_query_kernel.
 //   phase 2  descriptors are read POINT-MAJOR (feat_pm[B,N,ldf]).  A warp owns 32 consecutive slots:
 //            cp.async pulls 32 channels of four neighbours per instruction (8 lanes = one fully used
 //            128-byte run) into one of two private shared-memory tiles while the previous tile is
@@ -31,12 +32,10 @@ namespace {
 
 constexpr int kQgThreads = 256;
 constexpr int kQgWarps = 8;
-constexpr int kQgTile = 1024;      // xyz points per shared-memory tile (12 KB), double buffered
-constexpr int kQgBlock = 128;      // points per bounding-box block of a tile (8 blocks per tile)
+constexpr int kQgTile = 1024;      // (sizes the 24 KB box table: 1024 boxes of 6 floats)
 constexpr int kQgMaxSlots = 2048;  // slots (centres x nsample, both scales) per CTA
 constexpr int kQgTrStride = 36;    // floats per row of a per-warp [32 slots][32 channels] tile
 constexpr int kQgTrFloats = 32 * kQgTrStride;  // one tile; every warp owns two (double buffering)
-static_assert(kQgTile / kQgBlock == kQgWarps, "one bounding-box block per warp");
 static_assert(2 * kQgTrFloats >= 32 * 33, "scalar fallback transposes through the same buffer");
 
 struct QgScale {
@@ -48,6 +47,8 @@ struct QgScale {
 struct QgArgs {
   const float *xyz, *new_xyz, *feat;
   int ldf, n, m, c;
+  int blk;  // points per bounding-box block (multiple of 32; at most 896 blocks + their super boxes)
+  const float *boxes;  // [B][nblk + nsup][6] from qg_boxes_kernel
   QgScale s[2];
 };
 
@@ -167,6 +168,14 @@ __device__ __forceinline__ void qg_write_scale(const QgArgs &a, const QgScale &s
     }
     return;
   }
+  if (c <= 16) {
+    // few channels (level 1: rgb + normal): every slot walks its own short row
+    for (int s = t; s < nslots; s += kQgThreads) {
+      const float *row = feat_b + static_cast<size_t>(rows[s]) * a.ldf;
+      for (int ch = 0; ch < c; ++ch) stg_stream(out_f + ch * plane + s, __ldg(row + ch));
+    }
+    return;
+  }
   // generic rows (odd channel counts / unaligned strides): scalar 32x32 transposes
   for (int g = warp; g < ngroups; g += kQgWarps) {  // warp-uniform
     const int g0 = g * 32;
@@ -191,14 +200,70 @@ __device__ __forceinline__ void qg_write_scale(const QgArgs &a, const QgScale &s
   }
 }
 
+// Bounding boxes of every block of `blk` consecutive points (one warp per block) -- computed once per
+// cloud, not once per CTA.  Super boxes (8 blocks) are appended by qg_supboxes_kernel.
+__global__ void qg_boxes_kernel(const float *__restrict__ xyz, int n, int blk, int nblk, int nsup,
+                                float *__restrict__ boxes) {
+  const int b = blockIdx.y;
+  const unsigned lane = lane_id();
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (g >= nblk) return;
+  const float *cloud = xyz + static_cast<size_t>(b) * n * 3;
+  float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  const int k_end = min((g + 1) * blk, n);
+  for (int k = g * blk + static_cast<int>(lane); k < k_end; k += 32) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float v = __ldg(cloud + static_cast<size_t>(k) * 3 + d);
+      lo[d] = fminf(lo[d], v);
+      hi[d] = fmaxf(hi[d], v);
+      if (!(v == v)) { lo[d] = -3.0e38f; hi[d] = 3.0e38f; }  // NaN coordinate: never skip this block
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+      hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+    }
+  }
+  if (lane == 0) {
+    float *o = boxes + (static_cast<size_t>(b) * (nblk + nsup) + g) * 6;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      o[d] = lo[d];
+      o[3 + d] = hi[d];
+    }
+  }
+}
+__global__ void qg_supboxes_kernel(int nblk, int nsup, float *__restrict__ boxes) {
+  const int b = blockIdx.y;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nsup * 6) return;
+  float *base = boxes + static_cast<size_t>(b) * (nblk + nsup) * 6;
+  const int sb = e / 6, d = e % 6;
+  float v = base[(sb * 8) * 6 + d];
+  for (int i = 1; i < 8 && sb * 8 + i < nblk; ++i)
+    v = d < 3 ? fminf(v, base[(sb * 8 + i) * 6 + d]) : fmaxf(v, base[(sb * 8 + i) * 6 + d]);
+  base[(nblk + sb) * 6 + d] = v;
+}
+
+// squared distance between two axis-aligned boxes (0 when they overlap); b[0..2] = lo, b[3..5] = hi
+__device__ __forceinline__ float qg_box_dist2(const float (&u)[6], const float *b) {
+  const float ex = fmaxf(fmaxf(b[0] - u[3], u[0] - b[3]), 0.f);
+  const float ey = fmaxf(fmaxf(b[1] - u[4], u[1] - b[4]), 0.f);
+  const float ez = fmaxf(fmaxf(b[2] - u[5], u[2] - b[5]), 0.f);
+  return ex * ex + ey * ey + ez * ez;
+}
+
 template <int CW, bool DUAL>
 __global__ void __launch_bounds__(kQgThreads, 2) query_group_kernel(QgArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float *s_tile = reinterpret_cast<float *>(smem_raw);  // two tiles of kQgTile points
+  float *s_box = reinterpret_cast<float *>(smem_raw);  // [nblk][6] block boxes, then [nsup][6] super boxes
   int *s_rows = reinterpret_cast<int *>(smem_raw + QgSmem::tile_bytes);
   float *s_tr = reinterpret_cast<float *>(smem_raw + QgSmem::tile_bytes + QgSmem::rows_bytes);
-  __shared__ uint64_t s_bar[2];
-  __shared__ float s_bbox[kQgTile / kQgBlock][6];  // per 128-point block of the current tile
+  __shared__ int s_perm[32];  // scan slot -> local centre, sorted by y
 
   constexpr int TJ = kQgWarps * CW;
   const int b = blockIdx.y;
@@ -211,21 +276,54 @@ __global__ void __launch_bounds__(kQgThreads, 2) query_group_kernel(QgArgs a) {
   const float r2b = DUAL ? __fmul_rn(a.s[1].radius, a.s[1].radius) : 0.f;
   // a block can be skipped when even its bounding box is out of reach of the larger radius; the bound
   // is inflated so that fp32 rounding of the box distance can never hide a true hit
-  const float r2skip = fmaxf(r2a, r2b) * 1.0001f + 1e-12f;
+  const float r2max = fmaxf(r2a, r2b);
+  const float r2skip = r2max * 1.0001f + 1e-12f;
   int *rows_a = s_rows;             // [TJ][nsa]
   int *rows_b = s_rows + TJ * nsa;  // [TJ][nsb]
 
-  if (threadIdx.x == 0) {
-    mbar_init(&s_bar[0], 1);
-    mbar_init(&s_bar[1], 1);
-    mbar_fence_init();
+  // ---- bounding boxes of the cloud's blocks (a.blk points each) and of groups of 8 blocks -----------
+  const int blk = a.blk, nblk = (a.n + blk - 1) / blk, nsup = (nblk + 7) / 8;
+  float *s_sup = s_box + nblk * 6;
+  {
+    const float *src = a.boxes + static_cast<size_t>(b) * (nblk + nsup) * 6;
+    for (int e = threadIdx.x; e < (nblk + nsup) * 6; e += kQgThreads) s_box[e] = __ldg(src + e);
   }
-  // ---------------- phase 1: warp w scans for centres w*CW .. w*CW+CW-1 of the CTA ----------------
+  // The CTA's centres are dealt to the warps in order of their y coordinate, so that the CW centres a
+  // warp scans for together are close to each other and share the blocks they can skip (FPS order
+  // scatters consecutive centres all over the cloud).  Any assignment gives the same output.
+  if (warp == 0) {
+    const int lc0 = static_cast<int>(lane);
+    float key = (lc0 < live_centres) ? a.new_xyz[(static_cast<size_t>(b) * a.m + jc0 + lc0) * 3 + 1]
+                                     : __int_as_float(0x7f800000);
+    if (!(key == key)) key = __int_as_float(0x7f800000);  // NaN sorts last
+    int val = lc0;
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {  // bitonic sort of (key, val) across the warp
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        const float ok = __shfl_xor_sync(0xffffffffu, key, j);
+        const int ov = __shfl_xor_sync(0xffffffffu, val, j);
+        const bool up = ((lane & k) == 0);
+        const bool lower = ((lane & j) == 0);
+        const bool less = (ok < key) || (ok == key && ov < val);
+        const bool take = (lower == up) ? less : !less && !(ok == key && ov == val);
+        if (take) { key = ok; val = ov; }
+      }
+    }
+    s_perm[lane] = val;
+  }
+  __syncthreads();
+  // ---------------- phase 1: warp w scans for the centres in scan slots w*CW .. w*CW+CW-1 ------------
+  // No tile staging, no CTA barriers: every warp walks the cloud on its own (L1/L2-resident, 384
+  // contiguous bytes per step) and only where the box tests say a neighbour can be.
   float cx[CW], cy[CW], cz[CW];
-  int cnta[CW], firsta[CW], cntb[CW], firstb[CW];
+  int cnta[CW], firsta[CW], cntb[CW], firstb[CW], lcs[CW];
+  float ub[6] = {3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};  // box of the warp's centres
+  bool warp_open = false;
 #pragma unroll
   for (int q = 0; q < CW; ++q) {
-    const int lc = static_cast<int>(warp) * CW + q;
+    const int lc = s_perm[static_cast<int>(warp) * CW + q];
+    lcs[q] = lc;
     const bool live = lc < live_centres;
     const float *p = a.new_xyz + (static_cast<size_t>(b) * a.m + jc0 + (live ? lc : 0)) * 3;
     cx[q] = p[0];
@@ -234,123 +332,52 @@ __global__ void __launch_bounds__(kQgThreads, 2) query_group_kernel(QgArgs a) {
     cnta[q] = live ? 0 : nsa;  // dead centres count as full
     cntb[q] = live ? 0 : nsb;
     firsta[q] = firstb[q] = 0;
+    if (live) {
+      warp_open = true;
+      ub[0] = fminf(ub[0], cx[q]); ub[1] = fminf(ub[1], cy[q]); ub[2] = fminf(ub[2], cz[q]);
+      ub[3] = fmaxf(ub[3], cx[q]); ub[4] = fmaxf(ub[4], cy[q]); ub[5] = fmaxf(ub[5], cz[q]);
+      if (!(cx[q] == cx[q]) || !(cy[q] == cy[q]) || !(cz[q] == cz[q])) {  // NaN centre: no pruning
+        ub[0] = ub[1] = ub[2] = -3.0e38f;
+        ub[3] = ub[4] = ub[5] = 3.0e38f;
+      }
+    }
   }
-  __syncthreads();
-
-  // tile i lives in buffer i&1; the copy of tile i+1 is in flight while tile i is scanned
-  const int ntiles = (a.n + kQgTile - 1) / kQgTile;
-  const bool bulk = ((reinterpret_cast<uintptr_t>(cloud) & 15u) == 0);  // tile offsets are 16-B multiples
-  auto tile_count = [&](int i) { return min(kQgTile, a.n - i * kQgTile); };
-  auto issue_tile = [&](int i) {  // called by thread 0 (bulk) or by everyone (fallback)
-    const int cnt = tile_count(i);
-    const unsigned bytes = static_cast<unsigned>(cnt) * 12u;
-    float *dst = s_tile + (i & 1) * (kQgTile * 3);
-    const float *src = cloud + static_cast<size_t>(i) * kQgTile * 3;
-    if (bulk && (bytes & 15u) == 0u) {
-      if (threadIdx.x == 0) {
-        mbar_expect_tx(&s_bar[i & 1], bytes);
-        bulk_g2s(dst, src, bytes, &s_bar[i & 1]);
-      }
-    } else {
-      for (int e = threadIdx.x; e < cnt * 3; e += kQgThreads) dst[e] = __ldg(src + e);
-    }
-  };
-  auto wait_tile = [&](int i, unsigned (&ph)[2]) {
-    const unsigned bytes = static_cast<unsigned>(tile_count(i)) * 12u;
-    if (bulk && (bytes & 15u) == 0u) {
-      mbar_wait(&s_bar[i & 1], ph[i & 1]);
-      ph[i & 1] ^= 1u;
-    }
-  };
-  unsigned ph[2] = {0u, 0u};
-  bool warp_open = static_cast<int>(warp) * CW < live_centres;
-  issue_tile(0);
-  for (int ti = 0; ti < ntiles; ++ti) {
-    const int base = ti * kQgTile;
-    const int count = tile_count(ti);
-    const float *tile = s_tile + (ti & 1) * (kQgTile * 3);
-    if (ti + 1 < ntiles) issue_tile(ti + 1);  // buffer (ti+1)&1 was released by the barrier ending tile ti-1
-    wait_tile(ti, ph);
-    __syncthreads();  // fallback path: plain stores of tile ti visible (also orders s_bbox reuse)
-    // bounding box of every 128-point block: warp w takes block w
-    {
-      const int blk0 = static_cast<int>(warp) * kQgBlock;
-      float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-      for (int k = blk0 + static_cast<int>(lane); k < min(blk0 + kQgBlock, count); k += 32) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          const float v = tile[k * 3 + d];
-          lo[d] = fminf(lo[d], v);
-          hi[d] = fmaxf(hi[d], v);
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
-          hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
-        }
-      }
-      if (lane < 3) {
-        s_bbox[warp][lane] = lo[lane];
-        s_bbox[warp][3 + lane] = hi[lane];
-      }
-    }
-    __syncthreads();
-    if (warp_open) {
-      for (int blk = 0; blk * kQgBlock < count; ++blk) {
-        // distance from each centre to the block's box (0 inside); NaN coordinates fail the skip test
-        bool reach = false;
+  for (int sb = 0; sb < nsup && warp_open; ++sb) {
+    if (qg_box_dist2(ub, s_sup + sb * 6) > r2skip) continue;
+    const int g_end = min(sb * 8 + 8, nblk);
+    for (int g = sb * 8; g < g_end && warp_open; ++g) {
+      if (qg_box_dist2(ub, s_box + g * 6) > r2skip) continue;
+      const int k_end = min((g + 1) * blk, a.n);
+      for (int off = g * blk; off < k_end; off += 32) {
+        const int kk = off + static_cast<int>(lane);
+        const bool in = kk < k_end;
+        const float *pt = cloud + static_cast<size_t>(in ? kk : off) * 3;
+        const float x = __ldg(pt), y = __ldg(pt + 1), z = __ldg(pt + 2);
 #pragma unroll
         for (int q = 0; q < CW; ++q) {
-          const bool open_q = (cnta[q] < nsa) || (DUAL && cntb[q] < nsb);
-          const float ex = fmaxf(fmaxf(s_bbox[blk][0] - cx[q], cx[q] - s_bbox[blk][3]), 0.f);
-          const float ey = fmaxf(fmaxf(s_bbox[blk][1] - cy[q], cy[q] - s_bbox[blk][4]), 0.f);
-          const float ez = fmaxf(fmaxf(s_bbox[blk][2] - cz[q], cz[q] - s_bbox[blk][5]), 0.f);
-          reach |= open_q && !(ex * ex + ey * ey + ez * ez > r2skip);
-        }
-        if (!reach) continue;  // warp-uniform
-        const int off_end = min((blk + 1) * kQgBlock, count);
-        for (int off = blk * kQgBlock; off < off_end; off += 32) {
-          const int kk = off + static_cast<int>(lane);
-          const bool in = kk < count;
-          const float x = in ? tile[kk * 3 + 0] : 0.f;
-          const float y = in ? tile[kk * 3 + 1] : 0.f;
-          const float z = in ? tile[kk * 3 + 2] : 0.f;
-#pragma unroll
-          for (int q = 0; q < CW; ++q) {
-            const float d2 = ref_sqdist(cx[q] - x, cy[q] - y, cz[q] - z);
+          const float d2 = ref_sqdist(cx[q] - x, cy[q] - y, cz[q] - z);
+          // one ballot against the larger radius decides the common no-neighbour step
+          if (__ballot_sync(0xffffffffu, in && d2 < r2max)) {
             const unsigned ha = __ballot_sync(0xffffffffu, in && d2 < r2a);
             const unsigned hb = DUAL ? __ballot_sync(0xffffffffu, in && d2 < r2b) : 0u;
-            if (ha | hb) {  // rare: a step with a neighbour in it
-              const int lc = static_cast<int>(warp) * CW + q;
-              if (ha && cnta[q] < nsa)
-                qg_append(ha, cnta[q], firsta[q], nsa, rows_a + lc * nsa, base + off, lane);
-              if (DUAL && hb && cntb[q] < nsb)
-                qg_append(hb, cntb[q], firstb[q], nsb, rows_b + lc * nsb, base + off, lane);
-            }
+            if (ha && cnta[q] < nsa)
+              qg_append(ha, cnta[q], firsta[q], nsa, rows_a + lcs[q] * nsa, off, lane);
+            if (DUAL && hb && cntb[q] < nsb)
+              qg_append(hb, cntb[q], firstb[q], nsb, rows_b + lcs[q] * nsb, off, lane);
           }
         }
       }
       bool open = false;
 #pragma unroll
       for (int q = 0; q < CW; ++q) open |= (cnta[q] < nsa) || (DUAL && cntb[q] < nsb);
-      warp_open = open;
-    }
-    // barrier: tile consumed by every warp before its buffer is refilled; the OR tells all threads the
-    // same thing -- whether any ball of this CTA is still unfilled
-    if (!__syncthreads_or(warp_open ? 1 : 0)) {
-      // a copy of tile ti+1 may still be in flight: drain it before the buffer is reused / the CTA exits
-      if (ti + 1 < ntiles) wait_tile(ti + 1, ph);
-      break;
+      warp_open = open;  // every ball of this warp is full: nothing further can be appended
     }
   }
   // pad the rows: slots >= cnt repeat the first hit (0 for an empty ball: torch::zeros, ball_query.cpp:19)
   __syncwarp();
 #pragma unroll
   for (int q = 0; q < CW; ++q) {
-    const int lc = static_cast<int>(warp) * CW + q;
+    const int lc = lcs[q];
     if (lc < live_centres) {
       for (int s = min(cnta[q], nsa) + static_cast<int>(lane); s < nsa; s += 32) rows_a[lc * nsa + s] = firsta[q];
       if (DUAL)
@@ -377,11 +404,35 @@ int qg_launch(const QgArgs &a, int b, cudaStream_t st) {
   return check_launch("query_group_kernel");
 }
 
+int qg_dispatch_launch(QgArgs &a, int b, bool dual, cudaStream_t st);
+
 int qg_dispatch(QgArgs &a, int b, bool dual, cudaStream_t st) {
+  a.blk = 128;
+  while (ceil_div(a.n, a.blk) > 896) a.blk *= 2;  // box table lives in 24 KB of shared memory
+  const int nblk = ceil_div(a.n, a.blk), nsup = ceil_div(nblk, 8);
+  int rc0 = keep_async_pool_warm();
+  if (rc0 != PVN3D_OK) return rc0;
+  float *boxes = nullptr;  // stream-ordered scratch: [B][nblk+nsup][6] floats (2.6 KB per 12288-pt cloud)
+  PVN3D_CUDA_TRY(cudaMallocAsync(&boxes, sizeof(float) * 6 * static_cast<size_t>(b) * (nblk + nsup), st),
+                 "query_group box scratch");
+  qg_boxes_kernel<<<dim3(ceil_div(nblk, 8), b), 256, 0, st>>>(a.xyz, a.n, a.blk, nblk, nsup, boxes);
+  int rc = check_launch("qg_boxes_kernel");
+  if (rc == PVN3D_OK) {
+    qg_supboxes_kernel<<<dim3(ceil_div(nsup * 6, 128), b), 128, 0, st>>>(nblk, nsup, boxes);
+    rc = check_launch("qg_supboxes_kernel");
+  }
+  a.boxes = boxes;
+  if (rc == PVN3D_OK) rc = qg_dispatch_launch(a, b, dual, st);
+  cudaFreeAsync(boxes, st);
+  return rc;
+}
+
+int qg_dispatch_launch(QgArgs &a, int b, bool dual, cudaStream_t st) {
   const int ns_tot = a.s[0].ns + (dual ? a.s[1].ns : 0);
   // centres per warp: as many as fit the row buffer; big clouds amortise the scan over 4 centres
   int cw = 4;
-  if (a.n <= 4096) cw = 1;
+  if (a.n < 2048) cw = 2;
+  if (a.n < 1024) cw = 1;
   while (cw > 1 && kQgWarps * cw * ns_tot > kQgMaxSlots) cw >>= 1;
   if (kQgWarps * cw * ns_tot > kQgMaxSlots) return PVN3D_ERR_UNSUPPORTED;
   if (dual) {

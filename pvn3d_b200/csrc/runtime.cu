@@ -27,6 +27,20 @@ int sm_count() {
   return n;
 }
 
+int keep_async_pool_warm() {
+  // cudaMallocAsync scratch (query_group box tables, FPS fallback): by default the device pool hands
+  // memory back to the OS at every synchronisation, which makes the next allocation slow.  Keep it.
+  static PerDeviceOnce once;
+  if (!once.first_time()) return PVN3D_OK;
+  int dev = 0;
+  PVN3D_CUDA_TRY(cudaGetDevice(&dev), "cudaGetDevice");
+  cudaMemPool_t pool;
+  PVN3D_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev), "default mempool");
+  unsigned long long keep = ~0ull;
+  PVN3D_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep), "mempool threshold");
+  return PVN3D_OK;
+}
+
 int ref_opt_n_threads(int work_size) {
   // reference: cuda_utils.h:15-19 -- pow_2 = log(work)/log(2) truncated; clamp(1<<pow_2, 1, 512)
   const int pow_2 = static_cast<int>(std::log(static_cast<double>(work_size)) / std::log(2.0));
