@@ -184,6 +184,8 @@ def main():
     from pvn3d_b200 import _ext, _lib
     from pvn3d_b200.pipeline import FramePipeline
 
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"     # keep stdout to the single JSON line
     rank, local_rank, world = pdist.init_from_env()
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     dev = torch.device(f"cuda:{local_rank}")

@@ -254,23 +254,54 @@ __device__ __forceinline__ int ms_phase_end(int p) {  // last iteration of phase
   return p == 0 ? 6 : 16 * p;
 }
 
+// Shared-memory layout of a fit's points: point PAIRS, structure-of-arrays inside the pair
+//   s_pts[2p]   = (x0, x1, y0, y1)      s_pts[2p+1] = (z0, z1, w0, w1)       w = k |a'|^2
+// so that the sweep runs on the packed FP32 pipe (FFMA2 / FADD2: two points per instruction):
+// per point pair and seed 4 packed ops for the exponents, 2 MUFU.EX2, 4 packed ops to accumulate --
+// 5 issue slots per pair evaluation instead of 9.  An odd tail is padded with w = -inf (weight 0).
+__device__ __forceinline__ void ms_stage_pairs(float4 *s_pts, const float4 *__restrict__ cpts, int n) {
+  const int npairs = (n + 1) >> 1;
+  for (int q = threadIdx.x; q < npairs; q += kMsThreads) {
+    const float4 p0 = cpts[2 * q];
+    float4 p1 = make_float4(0.f, 0.f, 0.f, -__int_as_float(0x7f800000));
+    if (2 * q + 1 < n) p1 = cpts[2 * q + 1];
+    s_pts[2 * q] = make_float4(p0.x, p1.x, p0.y, p1.y);
+    s_pts[2 * q + 1] = make_float4(p0.z, p1.z, p0.w, p1.w);
+  }
+}
+
+struct MsSeedQ {  // per-seed constants of the exponent, duplicated into both halves of a pair
+  float2 qx, qy, qz, qw;
+};
+struct MsSeedS {  // packed partial sums (even points, odd points)
+  float2 sw, sx, sy, sz;
+};
+__device__ __forceinline__ MsSeedQ ms_seed_q(float k, float cx, float cy, float cz) {
+  MsSeedQ q;
+  const float x = -2.f * k * cx, y = -2.f * k * cy, z = -2.f * k * cz;
+  const float w = k * (cx * cx + cy * cy + cz * cz);
+  q.qx = make_float2(x, x); q.qy = make_float2(y, y); q.qz = make_float2(z, z); q.qw = make_float2(w, w);
+  return q;
+}
+__device__ __forceinline__ void ms_pair_step(const float4 &A, const float4 &B, const MsSeedQ &q, MsSeedS &s) {
+  const float2 x2 = make_float2(A.x, A.y), y2 = make_float2(A.z, A.w), z2 = make_float2(B.x, B.y),
+               w2 = make_float2(B.z, B.w);
+  const float2 e = __ffma2_rn(x2, q.qx, __ffma2_rn(y2, q.qy, __ffma2_rn(z2, q.qz, __fadd2_rn(w2, q.qw))));
+  const float2 w = make_float2(ex2_approx(e.x), ex2_approx(e.y));
+  s.sw = __fadd2_rn(s.sw, w);
+  s.sx = __ffma2_rn(w, x2, s.sx);
+  s.sy = __ffma2_rn(w, y2, s.sy);
+  s.sz = __ffma2_rn(w, z2, s.sz);
+}
+
 template <int R>
-__device__ __forceinline__ void ms_sweep(const float4 *__restrict__ s_pts, int n, const float (&qx)[R],
-                                         const float (&qy)[R], const float (&qz)[R],
-                                         const float (&qw)[R], float (&sw)[R], float (&sx)[R],
-                                         float (&sy)[R], float (&sz)[R]) {
-#pragma unroll 4
-  for (int j = 0; j < n; ++j) {
-    const float4 p = s_pts[j];  // broadcast LDS.128
+__device__ __forceinline__ void ms_sweep(const float4 *__restrict__ s_pts, int npairs, const MsSeedQ (&q)[R],
+                                         MsSeedS (&s)[R]) {
+#pragma unroll 2
+  for (int p = 0; p < npairs; ++p) {
+    const float4 A = s_pts[2 * p], B = s_pts[2 * p + 1];  // broadcast LDS.128 x2
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const float e = fmaf(p.x, qx[r], fmaf(p.y, qy[r], fmaf(p.z, qz[r], p.w + qw[r])));
-      const float w = ex2_approx(e);
-      sw[r] += w;
-      sx[r] = fmaf(w, p.x, sx[r]);
-      sy[r] = fmaf(w, p.y, sy[r]);
-      sz[r] = fmaf(w, p.z, sz[r]);
-    }
+    for (int r = 0; r < R; ++r) ms_pair_step(A, B, q[r], s[r]);
   }
 }
 
@@ -302,7 +333,7 @@ __device__ __forceinline__ void ms_run_tile(const MsArgs &a, MsIterSmem &sm, int
   }
   __syncthreads();  // previous tile's readers are done with sm.pts
   if (single) {
-    for (int q = t; q < n_c; q += kMsThreads) sm.pts[q] = a.cpts[start + q];
+    ms_stage_pairs(sm.pts, a.cpts + start, n_c);
     __syncthreads();
   }
 
@@ -313,24 +344,22 @@ __device__ __forceinline__ void ms_run_tile(const MsArgs &a, MsIterSmem &sm, int
     const bool warp_live = __any_sync(0xffffffffu, live);
     if (single && !warp_live) break;  // no barriers inside the loop in single-tile mode
 
-    float qx[R], qy[R], qz[R], qw[R], sw[R], sx[R], sy[R], sz[R];
+    MsSeedQ sq[R];
+    MsSeedS ss[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
-      qx[r] = -2.f * k * cx[r];
-      qy[r] = -2.f * k * cy[r];
-      qz[r] = -2.f * k * cz[r];
-      qw[r] = k * (cx[r] * cx[r] + cy[r] * cy[r] + cz[r] * cz[r]);
-      sw[r] = sx[r] = sy[r] = sz[r] = 0.f;
+      sq[r] = ms_seed_q(k, cx[r], cy[r], cz[r]);
+      ss[r].sw = ss[r].sx = ss[r].sy = ss[r].sz = make_float2(0.f, 0.f);
     }
     if (single) {
-      ms_sweep<R>(sm.pts, n_c, qx, qy, qz, qw, sw, sx, sy, sz);
+      ms_sweep<R>(sm.pts, (n_c + 1) >> 1, sq, ss);
     } else {
       for (int base = 0; base < n_c; base += kMsPtTile) {
         const int n = min(kMsPtTile, n_c - base);
         __syncthreads();
-        for (int q = t; q < n; q += kMsThreads) sm.pts[q] = a.cpts[start + base + q];
+        ms_stage_pairs(sm.pts, a.cpts + start + base, n);
         __syncthreads();
-        if (warp_live) ms_sweep<R>(sm.pts, n, qx, qy, qz, qw, sw, sx, sy, sz);
+        if (warp_live) ms_sweep<R>(sm.pts, (n + 1) >> 1, sq, ss);
       }
     }
     bool violates = false;
@@ -338,8 +367,9 @@ __device__ __forceinline__ void ms_run_tile(const MsArgs &a, MsIterSmem &sm, int
     for (int r = 0; r < R; ++r) {
       if (!frozen[r]) {
         // new_C = sum(w*A)/sum(w); Adis = |new_C - C|   (meanshift_pytorch.py:37-39)
-        const float nx = __fdiv_rn(sx[r], sw[r]), ny = __fdiv_rn(sy[r], sw[r]),
-                    nz = __fdiv_rn(sz[r], sw[r]);
+        const float swr = ss[r].sw.x + ss[r].sw.y;
+        const float nx = __fdiv_rn(ss[r].sx.x + ss[r].sx.y, swr), ny = __fdiv_rn(ss[r].sy.x + ss[r].sy.y, swr),
+                    nz = __fdiv_rn(ss[r].sz.x + ss[r].sz.y, swr);
         const float sh = __fsqrt_rn(torch_sqnorm(nx - cx[r], ny - cy[r], nz - cz[r]));
         cx[r] = nx; cy[r] = ny; cz[r] = nz; last[r] = sh;
         violates |= !(sh < a.stop_thresh);
@@ -383,8 +413,9 @@ __device__ __forceinline__ void ms_run_tile(const MsArgs &a, MsIterSmem &sm, int
 // the sweep (lane l takes points l, l+32, ...); the eight partial sums are combined with a butterfly
 // of warp shuffles, so every lane holds the same totals and the same new position.  Same work, 32x
 // shorter dependent chain, 32x more parallelism.
-constexpr int kMsSplitTile = 64;  // seeds per tile: 8 warps x 4 rounds x 2 seeds
-
+// SPW = seeds per warp (2 while there are plenty of seeds, 1 when fewer seeds than warps are left:
+// the late phases are pure latency -- a handful of creeping seeds, ~100 more iterations to go).
+template <int SPW>
 __device__ __forceinline__ void ms_run_tile_split(const MsArgs &a, MsIterSmem &sm, int f, int tile,
                                                   int it_lo, int it_hi, int cur, int nxt) {
   const int start = a.fit_start[f], n_c = a.fit_count[f];
@@ -400,100 +431,103 @@ __device__ __forceinline__ void ms_run_tile_split(const MsArgs &a, MsIterSmem &s
 
   __syncthreads();
   if (single) {
-    for (int q = t; q < n_c; q += kMsThreads) sm.pts[q] = a.cpts[start + q];
+    ms_stage_pairs(sm.pts, a.cpts + start, n_c);
     __syncthreads();
   }
-  // multi-tile fits need CTA-wide barriers inside the sweep, so all warps walk the rounds together
-  for (int round = 0; round < kMsSplitTile / (2 * kMsWarps); ++round) {
-    int idx[2];
-    float cx[2], cy[2], cz[2], last[2];
-    bool frozen[2];
+  int idx[SPW];
+  float cx[SPW], cy[SPW], cz[SPW], last[SPW];
+  bool frozen[SPW];
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int pos = tile * kMsSplitTile + round * (2 * kMsWarps) + 2 * warp + r;
-      const bool valid = pos < n_act;
-      idx[r] = valid ? act_cur[pos] : -1;
-      const float4 c = a.seeds[start + (valid ? idx[r] : 0)];
-      cx[r] = c.x; cy[r] = c.y; cz[r] = c.z; last[r] = c.w;
-      frozen[r] = !valid;
+  for (int r = 0; r < SPW; ++r) {
+    const int pos = tile * (kMsWarps * SPW) + SPW * warp + r;
+    const bool valid = pos < n_act;
+    idx[r] = valid ? act_cur[pos] : -1;
+    const float4 c = a.seeds[start + (valid ? idx[r] : 0)];
+    cx[r] = c.x; cy[r] = c.y; cz[r] = c.z; last[r] = c.w;
+    frozen[r] = !valid;
+  }
+  for (int it = it_lo; it <= it_hi; ++it) {
+    bool all_frozen = true;
+#pragma unroll
+    for (int r = 0; r < SPW; ++r) all_frozen &= frozen[r];
+    const bool warp_live = !all_frozen;  // warp-uniform
+    if (single && !warp_live) break;
+    MsSeedQ sq[SPW];
+    MsSeedS ss[SPW];
+#pragma unroll
+    for (int r = 0; r < SPW; ++r) {
+      sq[r] = ms_seed_q(k, cx[r], cy[r], cz[r]);
+      ss[r].sw = ss[r].sx = ss[r].sy = ss[r].sz = make_float2(0.f, 0.f);
     }
-    for (int it = it_lo; it <= it_hi; ++it) {
-      const bool warp_live = !(frozen[0] && frozen[1]);  // warp-uniform
-      if (single && !warp_live) break;
-      float qx[2], qy[2], qz[2], qw[2], sw[2], sx[2], sy[2], sz[2];
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        qx[r] = -2.f * k * cx[r];
-        qy[r] = -2.f * k * cy[r];
-        qz[r] = -2.f * k * cz[r];
-        qw[r] = k * (cx[r] * cx[r] + cy[r] * cy[r] + cz[r] * cz[r]);
-        sw[r] = sx[r] = sy[r] = sz[r] = 0.f;
-      }
-      for (int base = 0; base < n_c; base += kMsPtTile) {
-        const int n = min(kMsPtTile, n_c - base);
-        if (!single) {
-          __syncthreads();
-          for (int q = t; q < n; q += kMsThreads) sm.pts[q] = a.cpts[start + base + q];
-          __syncthreads();
-        }
-        if (warp_live) {
-#pragma unroll 4
-          for (int j = lane; j < n; j += 32) {
-            const float4 p = sm.pts[j];
-#pragma unroll
-            for (int r = 0; r < 2; ++r) {
-              const float e = fmaf(p.x, qx[r], fmaf(p.y, qy[r], fmaf(p.z, qz[r], p.w + qw[r])));
-              const float w = ex2_approx(e);
-              sw[r] += w;
-              sx[r] = fmaf(w, p.x, sx[r]);
-              sy[r] = fmaf(w, p.y, sy[r]);
-              sz[r] = fmaf(w, p.z, sz[r]);
-            }
-          }
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          sw[r] += __shfl_xor_sync(0xffffffffu, sw[r], o);
-          sx[r] += __shfl_xor_sync(0xffffffffu, sx[r], o);
-          sy[r] += __shfl_xor_sync(0xffffffffu, sy[r], o);
-          sz[r] += __shfl_xor_sync(0xffffffffu, sz[r], o);
-        }
-      }
-      bool violates = false;
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        if (!frozen[r]) {
-          const float nx = __fdiv_rn(sx[r], sw[r]), ny = __fdiv_rn(sy[r], sw[r]),
-                      nz = __fdiv_rn(sz[r], sw[r]);
-          const float sh = __fsqrt_rn(torch_sqnorm(nx - cx[r], ny - cy[r], nz - cz[r]));
-          cx[r] = nx; cy[r] = ny; cz[r] = nz; last[r] = sh;
-          violates |= !(sh < a.stop_thresh);
-          const bool still = sh < a.eps_stat;
-          if (idx[r] == star && lane == 0) {
-            a.traj[static_cast<size_t>(f) * a.traj_stride + it] = make_float4(nx, ny, nz, sh);
-            if (still && a.star_it[f] == 0) a.star_it[f] = it;
-          }
-          if (still && freeze_on) frozen[r] = true;
-        }
-      }
-      if (violates && lane == 0)
-        atomicOr(a.viol + static_cast<size_t>(f) * a.viol_words + (it >> 5), 1u << (it & 31));
+    for (int base = 0; base < n_c; base += kMsPtTile) {
+      const int n = min(kMsPtTile, n_c - base);
       if (!single) {
-        if (!__syncthreads_or((frozen[0] && frozen[1]) ? 0 : 1)) break;
+        __syncthreads();
+        ms_stage_pairs(sm.pts, a.cpts + start + base, n);
+        __syncthreads();
+      }
+      if (warp_live) {
+        const int npairs = (n + 1) >> 1;
+#pragma unroll 4
+        for (int p = lane; p < npairs; p += 32) {  // lane l takes point pairs l, l+32, ...
+          const float4 A = sm.pts[2 * p], B = sm.pts[2 * p + 1];
+#pragma unroll
+          for (int r = 0; r < SPW; ++r) ms_pair_step(A, B, sq[r], ss[r]);
+        }
       }
     }
-    if (lane == 0) {
+    float sw[SPW], sx[SPW], sy[SPW], sz[SPW];
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        if (idx[r] >= 0) {
-          a.seeds[start + idx[r]] = make_float4(cx[r], cy[r], cz[r], last[r]);
-          if (!frozen[r]) {
-            const int at = atomicAdd(a.act_cnt + static_cast<size_t>(nxt) * a.n_fits + f, 1);
-            act_nxt[at] = idx[r];
-          }
+    for (int r = 0; r < SPW; ++r) {
+      sw[r] = ss[r].sw.x + ss[r].sw.y;
+      sx[r] = ss[r].sx.x + ss[r].sx.y;
+      sy[r] = ss[r].sy.x + ss[r].sy.y;
+      sz[r] = ss[r].sz.x + ss[r].sz.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < SPW; ++r) {
+        sw[r] += __shfl_xor_sync(0xffffffffu, sw[r], o);
+        sx[r] += __shfl_xor_sync(0xffffffffu, sx[r], o);
+        sy[r] += __shfl_xor_sync(0xffffffffu, sy[r], o);
+        sz[r] += __shfl_xor_sync(0xffffffffu, sz[r], o);
+      }
+    }
+    bool violates = false;
+#pragma unroll
+    for (int r = 0; r < SPW; ++r) {
+      if (!frozen[r]) {
+        const float nx = __fdiv_rn(sx[r], sw[r]), ny = __fdiv_rn(sy[r], sw[r]),
+                    nz = __fdiv_rn(sz[r], sw[r]);
+        const float sh = __fsqrt_rn(torch_sqnorm(nx - cx[r], ny - cy[r], nz - cz[r]));
+        cx[r] = nx; cy[r] = ny; cz[r] = nz; last[r] = sh;
+        violates |= !(sh < a.stop_thresh);
+        const bool still = sh < a.eps_stat;
+        if (idx[r] == star && lane == 0) {
+          a.traj[static_cast<size_t>(f) * a.traj_stride + it] = make_float4(nx, ny, nz, sh);
+          if (still && a.star_it[f] == 0) a.star_it[f] = it;
+        }
+        if (still && freeze_on) frozen[r] = true;
+      }
+    }
+    if (violates && lane == 0)
+      atomicOr(a.viol + static_cast<size_t>(f) * a.viol_words + (it >> 5), 1u << (it & 31));
+    if (!single) {
+      bool fr = true;
+#pragma unroll
+      for (int r = 0; r < SPW; ++r) fr &= frozen[r];
+      if (!__syncthreads_or(fr ? 0 : 1)) break;
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < SPW; ++r) {
+      if (idx[r] >= 0) {
+        a.seeds[start + idx[r]] = make_float4(cx[r], cy[r], cz[r], last[r]);
+        if (!frozen[r]) {
+          const int at = atomicAdd(a.act_cnt + static_cast<size_t>(nxt) * a.n_fits + f, 1);
+          act_nxt[at] = idx[r];
         }
       }
     }
@@ -550,7 +584,8 @@ __global__ void __launch_bounds__(kMsThreads, 3) ms_iterate_kernel(MsArgs a) {
     int R = 2;
     if (total_seeds / (kMsThreads * R) < 2 * static_cast<int>(gridDim.x)) R = 1;
     const bool split = total_seeds < kMsThreads * static_cast<int>(gridDim.x);
-    const int tile_seeds = split ? kMsSplitTile : kMsThreads * R;
+    const int spw = (total_seeds <= kMsWarps * static_cast<int>(gridDim.x)) ? 1 : 2;  // split: seeds per warp
+    const int tile_seeds = split ? kMsWarps * spw : kMsThreads * R;
     int local_tiles = 0;
     for (int f = f_lo; f < f_hi; ++f) local_tiles += (sm.prefix[f] + tile_seeds - 1) / tile_seeds;
     int total;
@@ -563,6 +598,12 @@ __global__ void __launch_bounds__(kMsThreads, 3) ms_iterate_kernel(MsArgs a) {
     if (t == 0) sm.prefix[a.n_fits] = total;
     __syncthreads();
     if (blockIdx.x == 0 && t == 0) a.cfg[nxt] = 0;  // ticket counter of the next phase
+    if ((a.flags & 4u) && blockIdx.x == 0 && t == 0) {  // PVN3D_MS_DEBUG_TIMING
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      printf("[ms] phase %d it %d..%d seeds %d tiles %d R %d split %d t_us %llu\n", p, it_lo, it_hi,
+             total_seeds, total, R, split ? spw : 0, ns / 1000ull);
+    }
 
     // ---- tiles of this phase, handed out dynamically -------------------------------------------
     for (;;) {
@@ -573,7 +614,8 @@ __global__ void __launch_bounds__(kMsThreads, 3) ms_iterate_kernel(MsArgs a) {
       if (tk >= total) break;
       const int f = find_segment(sm.prefix, a.n_fits, tk);
       const int tile = tk - sm.prefix[f];
-      if (split) ms_run_tile_split(a, sm, f, tile, it_lo, it_hi, cur, nxt);
+      if (split && spw == 1) ms_run_tile_split<1>(a, sm, f, tile, it_lo, it_hi, cur, nxt);
+      else if (split) ms_run_tile_split<2>(a, sm, f, tile, it_lo, it_hi, cur, nxt);
       else if (R == 2) ms_run_tile<2>(a, sm, f, tile, it_lo, it_hi, cur, nxt);
       else ms_run_tile<1>(a, sm, f, tile, it_lo, it_hi, cur, nxt);
     }
