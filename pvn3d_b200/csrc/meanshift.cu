@@ -38,8 +38,11 @@ namespace {
 constexpr int kMsThreads = 256;
 constexpr int kMsFitMax = 2048;  // fits per launch chunk (prefix array lives in shared memory)
 constexpr int kMsPtTile = 4096;  // points per shared-memory tile of the sweep (64 KB)
+constexpr int kMsPairs = kMsPtTile / 2;
 constexpr int kMsDensTile = 1024;  // points per tile of the density pass (16 KB static)
 constexpr int kMsWarps = kMsThreads / 32;
+constexpr int kMsCfgInts = 4096;   // [0..2] phase tickets, [3] grid barrier, [4..2047] debug, [2048..] CTAs seen per SM
+constexpr int kMsCfgSm = 2048;
 
 struct MsArgs {
   const float4 *pts;
@@ -73,6 +76,7 @@ struct MsArgs {
   int cap;
   int viol_words;
   int traj_stride;
+  int ctas_per_sm;   // co-resident CTAs of ms_iterate_kernel per SM (grid = ctas_per_sm * #SM)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -148,10 +152,8 @@ __global__ void __launch_bounds__(1024) ms_setup_kernel(MsArgs a) {
     if (t == 0) s_run = run + total;
     __syncthreads();
   }
-  if (t == 0) {
-    a.dens_prefix[a.n_fits] = s_run;
-    a.cfg[0] = a.cfg[1] = a.cfg[2] = 0;
-  }
+  if (t == 0) a.dens_prefix[a.n_fits] = s_run;
+  for (int i = t; i < kMsCfgInts; i += 1024) a.cfg[i] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -242,6 +244,30 @@ __global__ void __launch_bounds__(kMsThreads) ms_prepare_kernel(MsArgs a) {
 // (tight cluster + 10 % outliers) need ~140 iterations by the reference's rule, but after the
 // first phase only the few creeping outlier seeds are still in the lists.
 // ------------------------------------------------------------------------------------------------
+// Grid-wide barrier for the persistent kernel (all CTAs co-resident: cooperative launch).  The
+// cooperative-groups grid.sync() spins on an acquire load, for which ptxas emits CCTL.IVALL (L1
+// invalidate) in the polling loop: CTAs that ran out of tiles then hammer the L1/shared-memory pipe
+// of their SM and slow the CTAs still sweeping by an order of magnitude (measured: 30 us per
+// iteration instead of ~1 us in the late phases).  Here idle CTAs poll a monotonically increasing
+// counter with relaxed loads and sleep in between; one fence pair orders the data.
+__device__ __forceinline__ void ms_grid_barrier(unsigned *counter, unsigned &epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();  // release: this CTA's global writes of the phase
+    const unsigned target = (epoch + 1u) * gridDim.x;
+    atomicAdd(counter, 1u);
+    unsigned seen;
+    for (;;) {
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+      if (seen >= target) break;
+      __nanosleep(256);
+    }
+    __threadfence();  // acquire: other CTAs' writes are visible from here on
+  }
+  ++epoch;
+  __syncthreads();
+}
+
 struct MsIterSmem {
   float4 pts[kMsPtTile];
   int prefix[kMsFitMax + 1];
@@ -255,7 +281,8 @@ __device__ __forceinline__ int ms_phase_end(int p) {  // last iteration of phase
 }
 
 // Shared-memory layout of a fit's points: point PAIRS, structure-of-arrays inside the pair
-//   s_pts[2p]   = (x0, x1, y0, y1)      s_pts[2p+1] = (z0, z1, w0, w1)       w = k |a'|^2
+//   s_pts[p] = (x0, x1, y0, y1)      s_pts[kMsPairs + p] = (z0, z1, w0, w1)       w = k |a'|^2
+// (two planes, so that a warp whose lanes read CONSECUTIVE pairs touches every bank once)
 // so that the sweep runs on the packed FP32 pipe (FFMA2 / FADD2: two points per instruction):
 // per point pair and seed 4 packed ops for the exponents, 2 MUFU.EX2, 4 packed ops to accumulate --
 // 5 issue slots per pair evaluation instead of 9.  An odd tail is padded with w = -inf (weight 0).
@@ -265,8 +292,8 @@ __device__ __forceinline__ void ms_stage_pairs(float4 *s_pts, const float4 *__re
     const float4 p0 = cpts[2 * q];
     float4 p1 = make_float4(0.f, 0.f, 0.f, -__int_as_float(0x7f800000));
     if (2 * q + 1 < n) p1 = cpts[2 * q + 1];
-    s_pts[2 * q] = make_float4(p0.x, p1.x, p0.y, p1.y);
-    s_pts[2 * q + 1] = make_float4(p0.z, p1.z, p0.w, p1.w);
+    s_pts[q] = make_float4(p0.x, p1.x, p0.y, p1.y);
+    s_pts[kMsPairs + q] = make_float4(p0.z, p1.z, p0.w, p1.w);
   }
 }
 
@@ -299,7 +326,7 @@ __device__ __forceinline__ void ms_sweep(const float4 *__restrict__ s_pts, int n
                                          MsSeedS (&s)[R]) {
 #pragma unroll 2
   for (int p = 0; p < npairs; ++p) {
-    const float4 A = s_pts[2 * p], B = s_pts[2 * p + 1];  // broadcast LDS.128 x2
+    const float4 A = s_pts[p], B = s_pts[kMsPairs + p];  // broadcast LDS.128 x2
 #pragma unroll
     for (int r = 0; r < R; ++r) ms_pair_step(A, B, q[r], s[r]);
   }
@@ -413,17 +440,26 @@ __device__ __forceinline__ void ms_run_tile(const MsArgs &a, MsIterSmem &sm, int
 // the sweep (lane l takes points l, l+32, ...); the eight partial sums are combined with a butterfly
 // of warp shuffles, so every lane holds the same totals and the same new position.  Same work, 32x
 // shorter dependent chain, 32x more parallelism.
-// SPW = seeds per warp (2 while there are plenty of seeds, 1 when fewer seeds than warps are left:
-// the late phases are pure latency -- a handful of creeping seeds, ~100 more iterations to go).
-template <int SPW>
+// Warp layout <L, SPL>: a warp is 32/L groups of L lanes; every group owns SPL seeds and its L lanes
+// share the sweep (lane j of the group takes point pairs j, j+L, ...).  Seeds per warp = 32/L * SPL:
+//   <4,2> = 16 seeds: lanes of different groups read the SAME point pair (shared-memory broadcast), so
+//           a sweep step costs 2 wavefronts instead of 16 -- the throughput layout while thousands of
+//           seeds are left;
+//   <32,1> = 1 seed: the shortest dependent chain (n_c/64 steps) -- the latency layout for the last,
+//           nearly empty phases.
+template <int L, int SPL>
 __device__ __forceinline__ void ms_run_tile_split(const MsArgs &a, MsIterSmem &sm, int f, int tile,
-                                                  int it_lo, int it_hi, int cur, int nxt) {
+                                                  int it_lo, int it_hi, int cur, int nxt,
+                                                  int warps_live = kMsWarps) {
+  constexpr int kGroups = 32 / L;
+  constexpr int kSeedsPerWarp = kGroups * SPL;
   const int start = a.fit_start[f], n_c = a.fit_count[f];
   const int n_act = a.act_cnt[static_cast<size_t>(cur) * a.n_fits + f];
   const int *act_cur = a.act + static_cast<size_t>(cur) * a.cap + start;
   int *act_nxt = a.act + static_cast<size_t>(nxt) * a.cap + start;
   const int t = threadIdx.x;
   const unsigned lane = t & 31u, warp = t >> 5;
+  const int grp = static_cast<int>(lane) / L, sub = static_cast<int>(lane) % L;
   const float k = a.kexp;
   const bool single = n_c <= kMsPtTile;
   const bool freeze_on = !(a.flags & PVN3D_MS_NO_FREEZE);
@@ -434,28 +470,34 @@ __device__ __forceinline__ void ms_run_tile_split(const MsArgs &a, MsIterSmem &s
     ms_stage_pairs(sm.pts, a.cpts + start, n_c);
     __syncthreads();
   }
-  int idx[SPW];
-  float cx[SPW], cy[SPW], cz[SPW], last[SPW];
-  bool frozen[SPW];
+  const bool dbg = (a.flags & 4u) && it_lo == 209 && t == 0;
+  unsigned long long dbg_t0 = 0;
+  int dbg_c[3] = {0, 0, 0};
+  if (dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+  int idx[SPL];
+  float cx[SPL], cy[SPL], cz[SPL], last[SPL];
+  bool frozen[SPL];
 #pragma unroll
-  for (int r = 0; r < SPW; ++r) {
-    const int pos = tile * (kMsWarps * SPW) + SPW * warp + r;
-    const bool valid = pos < n_act;
+  for (int r = 0; r < SPL; ++r) {
+    const int pos = (tile * warps_live + static_cast<int>(warp)) * kSeedsPerWarp + r * kGroups + grp;
+    const bool valid = static_cast<int>(warp) < warps_live && pos < n_act;
     idx[r] = valid ? act_cur[pos] : -1;
     const float4 c = a.seeds[start + (valid ? idx[r] : 0)];
     cx[r] = c.x; cy[r] = c.y; cz[r] = c.z; last[r] = c.w;
     frozen[r] = !valid;
   }
   for (int it = it_lo; it <= it_hi; ++it) {
-    bool all_frozen = true;
+    bool mine_frozen = true;
 #pragma unroll
-    for (int r = 0; r < SPW; ++r) all_frozen &= frozen[r];
-    const bool warp_live = !all_frozen;  // warp-uniform
+    for (int r = 0; r < SPL; ++r) mine_frozen &= frozen[r];
+    const bool warp_live = !__all_sync(0xffffffffu, mine_frozen);
     if (single && !warp_live) break;
-    MsSeedQ sq[SPW];
-    MsSeedS ss[SPW];
+    MsSeedQ sq[SPL];
+    MsSeedS ss[SPL];
+    long long ck0 = 0, ck1 = 0, ck2 = 0;
+    if (dbg) ck0 = clock64();
 #pragma unroll
-    for (int r = 0; r < SPW; ++r) {
+    for (int r = 0; r < SPL; ++r) {
       sq[r] = ms_seed_q(k, cx[r], cy[r], cz[r]);
       ss[r].sw = ss[r].sx = ss[r].sy = ss[r].sz = make_float2(0.f, 0.f);
     }
@@ -469,34 +511,36 @@ __device__ __forceinline__ void ms_run_tile_split(const MsArgs &a, MsIterSmem &s
       if (warp_live) {
         const int npairs = (n + 1) >> 1;
 #pragma unroll 4
-        for (int p = lane; p < npairs; p += 32) {  // lane l takes point pairs l, l+32, ...
-          const float4 A = sm.pts[2 * p], B = sm.pts[2 * p + 1];
+        for (int p = sub; p < npairs; p += L) {
+          const float4 A = sm.pts[p], B = sm.pts[kMsPairs + p];
 #pragma unroll
-          for (int r = 0; r < SPW; ++r) ms_pair_step(A, B, sq[r], ss[r]);
+          for (int r = 0; r < SPL; ++r) ms_pair_step(A, B, sq[r], ss[r]);
         }
       }
     }
-    float sw[SPW], sx[SPW], sy[SPW], sz[SPW];
+    if (dbg) ck1 = clock64();
+    float sw[SPL], sx[SPL], sy[SPL], sz[SPL];
 #pragma unroll
-    for (int r = 0; r < SPW; ++r) {
+    for (int r = 0; r < SPL; ++r) {
       sw[r] = ss[r].sw.x + ss[r].sw.y;
       sx[r] = ss[r].sx.x + ss[r].sx.y;
       sy[r] = ss[r].sy.x + ss[r].sy.y;
       sz[r] = ss[r].sz.x + ss[r].sz.y;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
+    for (int o = L / 2; o > 0; o >>= 1) {  // butterfly inside the group: every lane gets the totals
 #pragma unroll
-      for (int r = 0; r < SPW; ++r) {
+      for (int r = 0; r < SPL; ++r) {
         sw[r] += __shfl_xor_sync(0xffffffffu, sw[r], o);
         sx[r] += __shfl_xor_sync(0xffffffffu, sx[r], o);
         sy[r] += __shfl_xor_sync(0xffffffffu, sy[r], o);
         sz[r] += __shfl_xor_sync(0xffffffffu, sz[r], o);
       }
     }
+    if (dbg) ck2 = clock64();
     bool violates = false;
 #pragma unroll
-    for (int r = 0; r < SPW; ++r) {
+    for (int r = 0; r < SPL; ++r) {
       if (!frozen[r]) {
         const float nx = __fdiv_rn(sx[r], sw[r]), ny = __fdiv_rn(sy[r], sw[r]),
                     nz = __fdiv_rn(sz[r], sw[r]);
@@ -504,25 +548,42 @@ __device__ __forceinline__ void ms_run_tile_split(const MsArgs &a, MsIterSmem &s
         cx[r] = nx; cy[r] = ny; cz[r] = nz; last[r] = sh;
         violates |= !(sh < a.stop_thresh);
         const bool still = sh < a.eps_stat;
-        if (idx[r] == star && lane == 0) {
+        if (idx[r] == star && sub == 0) {
           a.traj[static_cast<size_t>(f) * a.traj_stride + it] = make_float4(nx, ny, nz, sh);
           if (still && a.star_it[f] == 0) a.star_it[f] = it;
         }
         if (still && freeze_on) frozen[r] = true;
       }
     }
-    if (violates && lane == 0)
+    if (__any_sync(0xffffffffu, violates) && lane == 0)
       atomicOr(a.viol + static_cast<size_t>(f) * a.viol_words + (it >> 5), 1u << (it & 31));
+    if (dbg && it == it_lo) {
+      dbg_c[0] = static_cast<int>(ck1 - ck0);
+      dbg_c[1] = static_cast<int>(ck2 - ck1);
+      dbg_c[2] = static_cast<int>(clock64() - ck2);
+    }
     if (!single) {
       bool fr = true;
 #pragma unroll
-      for (int r = 0; r < SPW; ++r) fr &= frozen[r];
+      for (int r = 0; r < SPL; ++r) fr &= frozen[r];
       if (!__syncthreads_or(fr ? 0 : 1)) break;
     }
   }
-  if (lane == 0) {
+  if (dbg) {
+    unsigned long long ns;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+    const int slot = atomicAdd(a.cfg + 4, 1);
+    if (slot < 220) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      int *rec = a.cfg + 256 + 8 * slot;
+      rec[0] = f; rec[1] = tile; rec[2] = n_c; rec[3] = n_act; rec[4] = static_cast<int>(smid);
+      rec[5] = static_cast<int>(ns - dbg_t0); rec[6] = dbg_c[0]; rec[7] = dbg_c[1];
+    }
+  }
+  if (sub == 0) {
 #pragma unroll
-    for (int r = 0; r < SPW; ++r) {
+    for (int r = 0; r < SPL; ++r) {
       if (idx[r] >= 0) {
         a.seeds[start + idx[r]] = make_float4(cx[r], cy[r], cz[r], last[r]);
         if (!frozen[r]) {
@@ -537,12 +598,24 @@ __device__ __forceinline__ void ms_run_tile_split(const MsArgs &a, MsIterSmem &s
 __global__ void __launch_bounds__(kMsThreads, 3) ms_iterate_kernel(MsArgs a) {
   extern __shared__ __align__(16) unsigned char ms_smem_raw[];
   MsIterSmem &sm = *reinterpret_cast<MsIterSmem *>(ms_smem_raw);
-  cg::grid_group grid = cg::this_grid();
+  unsigned epoch = 0;
+  unsigned *gbar = reinterpret_cast<unsigned *>(a.cfg + 3);  // zeroed by ms_setup_kernel
   const int t = threadIdx.x;
   const int per_thread = (a.n_fits + kMsThreads - 1) / kMsThreads;  // <= 8
   const int f_lo = min(a.n_fits, t * per_thread), f_hi = min(a.n_fits, f_lo + per_thread);
   const int last_it = a.max_iter + 1;  // the reference breaks when it > max_iter (:42)
   const bool early = a.flags & PVN3D_MS_EARLY_EXIT;
+  // rank of this CTA among the CTAs resident on its SM: phases with few tiles hand them to rank 0
+  // first, so that the tiles land on DIFFERENT SMs (a tile is bound by its SM's MUFU / LDS rate)
+  if (t == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    sm.ticket = atomicAdd(a.cfg + kMsCfgSm + static_cast<int>(smid & 1023u), 1);
+  }
+  __syncthreads();
+  const int sm_rank = sm.ticket;
+  const int n_sm = max(1, static_cast<int>(gridDim.x) / max(1, a.ctas_per_sm));
+  __syncthreads();
 
   for (int p = 0;; ++p) {
     const int cur = p % 3, nxt = (p + 1) % 3, nxt2 = (p + 2) % 3;
@@ -584,8 +657,15 @@ __global__ void __launch_bounds__(kMsThreads, 3) ms_iterate_kernel(MsArgs a) {
     int R = 2;
     if (total_seeds / (kMsThreads * R) < 2 * static_cast<int>(gridDim.x)) R = 1;
     const bool split = total_seeds < kMsThreads * static_cast<int>(gridDim.x);
-    const int spw = (total_seeds <= kMsWarps * static_cast<int>(gridDim.x)) ? 1 : 2;  // split: seeds per warp
-    const int tile_seeds = split ? kMsWarps * spw : kMsThreads * R;
+    // split sweep: seeds per warp (16, 8, 4, 2, 1) -- as many as keeps every warp of the grid busy
+    const int warps_total = kMsWarps * static_cast<int>(gridDim.x);
+    int spw = 16;
+    while (spw > 1 && total_seeds < spw * warps_total) spw >>= 1;
+    // last phases: fewer seeds than warps on one CTA per SM -> smaller tiles (1, 2 or 4 live warps)
+    int warps_live = kMsWarps;
+    if (split && spw == 1)
+      while (warps_live > 1 && total_seeds < warps_live * n_sm) warps_live >>= 1;
+    const int tile_seeds = split ? warps_live * spw : kMsThreads * R;
     int local_tiles = 0;
     for (int f = f_lo; f < f_hi; ++f) local_tiles += (sm.prefix[f] + tile_seeds - 1) / tile_seeds;
     int total;
@@ -598,15 +678,17 @@ __global__ void __launch_bounds__(kMsThreads, 3) ms_iterate_kernel(MsArgs a) {
     if (t == 0) sm.prefix[a.n_fits] = total;
     __syncthreads();
     if (blockIdx.x == 0 && t == 0) a.cfg[nxt] = 0;  // ticket counter of the next phase
-    if ((a.flags & 4u) && blockIdx.x == 0 && t == 0) {  // PVN3D_MS_DEBUG_TIMING
+    if ((a.flags & 4u) && blockIdx.x == 0 && t == 0 && p < 60) {  // PVN3D_MS_DEBUG_TIMING: stamps in cfg
       unsigned long long ns;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
-      printf("[ms] phase %d it %d..%d seeds %d tiles %d R %d split %d t_us %llu\n", p, it_lo, it_hi,
-             total_seeds, total, R, split ? spw : 0, ns / 1000ull);
+      a.cfg[16 + p] = static_cast<int>((ns / 1000ull) & 0x3fffffffull);  // top of phase p (us)
+      a.cfg[136 + p] = total_seeds;
+      a.cfg[196 + p] = total;
     }
 
     // ---- tiles of this phase, handed out dynamically -------------------------------------------
-    for (;;) {
+    const bool takes_tiles = static_cast<long long>(sm_rank) * n_sm < total;
+    for (; takes_tiles;) {
       if (t == 0) sm.ticket = atomicAdd(a.cfg + cur, 1);
       __syncthreads();
       const int tk = sm.ticket;
@@ -614,12 +696,20 @@ __global__ void __launch_bounds__(kMsThreads, 3) ms_iterate_kernel(MsArgs a) {
       if (tk >= total) break;
       const int f = find_segment(sm.prefix, a.n_fits, tk);
       const int tile = tk - sm.prefix[f];
-      if (split && spw == 1) ms_run_tile_split<1>(a, sm, f, tile, it_lo, it_hi, cur, nxt);
-      else if (split) ms_run_tile_split<2>(a, sm, f, tile, it_lo, it_hi, cur, nxt);
+      if (split && spw == 16) ms_run_tile_split<4, 2>(a, sm, f, tile, it_lo, it_hi, cur, nxt);
+      else if (split && spw == 8) ms_run_tile_split<8, 2>(a, sm, f, tile, it_lo, it_hi, cur, nxt);
+      else if (split && spw == 4) ms_run_tile_split<16, 2>(a, sm, f, tile, it_lo, it_hi, cur, nxt);
+      else if (split && spw == 2) ms_run_tile_split<32, 2>(a, sm, f, tile, it_lo, it_hi, cur, nxt);
+      else if (split) ms_run_tile_split<32, 1>(a, sm, f, tile, it_lo, it_hi, cur, nxt, warps_live);
       else if (R == 2) ms_run_tile<2>(a, sm, f, tile, it_lo, it_hi, cur, nxt);
       else ms_run_tile<1>(a, sm, f, tile, it_lo, it_hi, cur, nxt);
     }
-    grid.sync();
+    if ((a.flags & 4u) && t == 0) {
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+      if (p < 60) atomicMax(a.cfg + 76 + p, static_cast<int>((ns / 1000ull) & 0x3fffffffull));  // tiles done
+    }
+    ms_grid_barrier(gbar, epoch);
   }
 
   // ---- results: C[max_idx] after exactly T iterations, back in world coordinates (:51) -----------
@@ -658,6 +748,7 @@ MsLayout ms_layout(int cap, int n_fits, int max_iter) {
     return at;
   };
   const size_t nf = n_fits > 0 ? n_fits : 1, cp = cap > 0 ? cap : 1;
+  L.cfg = take(kMsCfgInts * sizeof(int));  // first: debug stamps are read back from the head of the workspace
   L.cpts = take(cp * sizeof(float4));
   L.seeds = take(cp * sizeof(float4));
   L.viol_words = (max_iter + 2 + 31) / 32;
@@ -671,17 +762,17 @@ MsLayout ms_layout(int cap, int n_fits, int max_iter) {
   L.viol = take(nf * L.viol_words * sizeof(unsigned));
   L.traj = take(nf * static_cast<size_t>(L.traj_stride) * sizeof(float4));
   L.dens_prefix = take((nf + 1) * sizeof(int));
-  L.cfg = take(16 * sizeof(int));
   L.total = off;
   return L;
 }
 
-int ms_persistent_grid(int *out) {
-  static int cached[64] = {0};
+int ms_persistent_grid(int *out, int *ctas_per_sm) {
+  static int cached[64] = {0}, cached_per_sm[64] = {0};
   int dev = 0;
   PVN3D_CUDA_TRY(cudaGetDevice(&dev), "cudaGetDevice");
   if (dev >= 0 && dev < 64 && cached[dev] > 0) {
     *out = cached[dev];
+    *ctas_per_sm = cached_per_sm[dev];
     return PVN3D_OK;
   }
   PVN3D_CUDA_TRY(cudaFuncSetAttribute(ms_iterate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -694,7 +785,11 @@ int ms_persistent_grid(int *out) {
   PVN3D_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev), "sm count");
   if (per_sm < 1 || sms < 1) return PVN3D_ERR_UNSUPPORTED;
   *out = per_sm * sms;
-  if (dev >= 0 && dev < 64) cached[dev] = *out;
+  *ctas_per_sm = per_sm;
+  if (dev >= 0 && dev < 64) {
+    cached_per_sm[dev] = per_sm;
+    cached[dev] = *out;
+  }
   return PVN3D_OK;
 }
 
@@ -707,8 +802,8 @@ int meanshift_launch(const float4 *pts, const int *fit_start, const int *fit_cou
                      uint8_t *labels, int *max_idx, int *n_in, unsigned char *ws, cudaStream_t st,
                      bool density_only) {
   if (n_fits <= 0) return PVN3D_OK;
-  int grid = 0;
-  int rc = ms_persistent_grid(&grid);
+  int grid = 0, per_sm = 1;
+  int rc = ms_persistent_grid(&grid, &per_sm);
   if (rc != PVN3D_OK) return rc;
   const float bwf = static_cast<float>(bandwidth);
   const MsLayout L = ms_layout(cap, n_fits, max_iter);
@@ -744,6 +839,7 @@ int meanshift_launch(const float4 *pts, const int *fit_start, const int *fit_cou
     a.cap = cap;
     a.viol_words = L.viol_words;
     a.traj_stride = L.traj_stride;
+    a.ctas_per_sm = per_sm;
 
     ms_setup_kernel<<<1, 1024, 0, st>>>(a);
     if ((rc = check_launch("ms_setup_kernel")) != PVN3D_OK) return rc;

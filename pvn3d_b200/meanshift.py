@@ -33,6 +33,7 @@ class MeanShiftTorch:
         #: validation switch: sweep every seed at every iteration like the reference does, instead of
         #: dropping seeds that have stopped moving (shift < 1e-6*bandwidth) from the work lists
         self.no_freeze = no_freeze
+        self.debug_timing = False
         self.last_iters = None  # iteration count(s) of the last call, device tensor
 
     # ---- reference surface -------------------------------------------------------------------
@@ -84,7 +85,7 @@ class MeanShiftTorch:
             raise ValueError("max_iter must be in [0, 4094]")
         ws = torch.empty((ws_bytes + 256,), dtype=torch.uint8, device=dev)
         ws_ptr = (ws.data_ptr() + 255) // 256 * 256
-        flags = (PVN3D_MS_EARLY_EXIT if self.early_exit else PVN3D_MS_STRICT) | (PVN3D_MS_NO_FREEZE if self.no_freeze else 0)
+        flags = (PVN3D_MS_EARLY_EXIT if self.early_exit else PVN3D_MS_STRICT) | (PVN3D_MS_NO_FREEZE if self.no_freeze else 0) | (4 if self.debug_timing else 0)
         with torch.cuda.device(dev):
             rc = lib.pvn3d_meanshift_fit_batch(
                 ptr(pts4), ptr(fit_start), ptr(fit_count), nf, cap, float(self.bandwidth),
@@ -92,5 +93,6 @@ class MeanShiftTorch:
                 ws_ptr, ws_bytes, torch.cuda.current_stream(dev).cuda_stream)
         check(rc, "pvn3d_meanshift_fit_batch")
         ws.record_stream(torch.cuda.current_stream(dev))
+        self._last_ws = (ws, ws_ptr - ws.data_ptr())   # debug: phase stamps live in the first 1 KB
         self.last_iters = ctr[:, 3]
         return ctr, labels, max_idx, n_in

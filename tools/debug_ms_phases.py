@@ -1,19 +1,41 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from pvn3d_b200 import synth, fixtures
-from pvn3d_b200.eval_utils import FramePoseSolver
+from pvn3d_b200 import synth
+from pvn3d_b200.meanshift import MeanShiftTorch
 dev = torch.device("cuda:0")
 B = 32
 frames = synth.make_batch("linemod", B, n_points=12288, config_id=2, lm_obj_id=1)
-st = synth.stack(frames)
-d = {k: torch.from_numpy(v).to(dev) for k, v in st.items()}
-s = FramePoseSolver(B, 12288, 8, 2, fixtures.mesh_kps_table_lm(1), None, False, device=dev)
+clouds = []
+for f in frames:
+    sel = f.labels == 1
+    clouds.append(torch.from_numpy(f.pcld[sel] - f.ctr_of[0][sel]))
+    for k in range(8):
+        clouds.append(torch.from_numpy(f.pcld[sel] - f.kp_of[k][sel]))
+counts = [c.shape[0] for c in clouds]
+total = sum(counts)
+pts = torch.zeros(total, 4)
+pts[:, :3] = torch.cat(clouds)
+pts = pts.to(dev)
+starts = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int32)
+fs = torch.from_numpy(starts).to(dev); fc = torch.tensor(counts, dtype=torch.int32, device=dev)
+ms = MeanShiftTorch(0.08)
 for i in range(2):
-    s.solve(d["pcld"], d["labels"], d["ctr_of"], d["kp_of"])
+    ms.fit_segments(pts, fs, fc, want_labels=False)
 torch.cuda.synchronize()
-s.flags |= 4
+ms.debug_timing = True
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record(); s.solve(d["pcld"], d["labels"], d["ctr_of"], d["kp_of"]); e1.record()
+e0.record(); ctr, _, _, _ = ms.fit_segments(pts, fs, fc, want_labels=False); e1.record()
 torch.cuda.synchronize()
-print("solve ms", e0.elapsed_time(e1))
+print("fits", len(counts), "points", total, "total ms", e0.elapsed_time(e1), "iters min/mean/max", ctr[:,3].min().item(), ctr[:,3].mean().item(), ctr[:,3].max().item())
+ws, off = ms._last_ws
+cfg = ws[off:off + 8192].view(torch.int32).cpu().numpy()
+top, done, seeds, tiles = cfg[16:76], cfg[76:136], cfg[136:196], cfg[196:256]
+for p in range(60):
+    if top[p] == 0: break
+    nxt = top[p + 1] if p + 1 < 60 and top[p + 1] else done[p]
+    print(f"phase {p:2d} seeds {seeds[p]:7d} tiles {tiles[p]:5d}  tiles {done[p]-top[p]:6d} us   sync+top {nxt-done[p]:5d} us")
+n = min(int(cfg[4]), 220)
+rec = cfg[256:256 + 8 * n].reshape(n, 8)
+print("probe tiles of the phase starting at it 209:", n, " columns: f tile n_c n_act smid total_ns sweep_cyc reduce_cyc")
+print(rec[np.argsort(rec[:, 5])][-40:])
