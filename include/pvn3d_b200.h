@@ -146,11 +146,19 @@ int pvn3d_three_nn_interpolate(const float *unknown, const float *known, const f
  *        (k_pad multiple of 32, n_pad multiple of 16); bias [n_pad] (folded BN shift, 0 in the pad)
  *   out  point-major rows of length ldo (ldo, col0 multiples of 4); pool in {0, 8, 16, 32}
  * Arithmetic: TF32 operands (round-to-nearest), fp32 accumulation in TMEM.
+ * flags: PVN3D_MLP_RELU       apply ReLU (flags = 1 / 0 is the plain relu switch)
+ *        PVN3D_MLP_ROUND_OUT  store the activations already rounded to TF32 (ignored with pool)
+ *        PVN3D_MLP_A_TF32     (mlp_dense) `a` was produced with ROUND_OUT and is 16-byte aligned with
+ *                             lda % 4 == 0: it is copied global -> shared asynchronously, without the
+ *                             rounding pass (an unrounded `a` would be TRUNCATED by the tensor core)
  * ---------------------------------------------------------------------------------------- */
+#define PVN3D_MLP_RELU 1
+#define PVN3D_MLP_ROUND_OUT 2
+#define PVN3D_MLP_A_TF32 4
 
 /* A = point-major activations a[rows, lda]; columns >= a_cols read as zero. */
 int pvn3d_mlp_dense(const float *a, int lda, int a_cols, long long rows, const float *w,
-                    const float *bias, int k_pad, int n_pad, int relu, int pool, float *out, int ldo,
+                    const float *bias, int k_pad, int n_pad, int flags, int pool, float *out, int ldo,
                     int col0, pvn3d_stream_t stream);
 /* First layer of one SA scale with QueryAndGroup fused into the operand producer: row (b,j,s) =
  * [ feat_pm[b, idx[b,j,s], 0:c_feat] | xyz[b,idx] - new_xyz[b,j] | 0.. ]  -- NOTE the column order:
@@ -158,13 +166,13 @@ int pvn3d_mlp_dense(const float *a, int lda, int a_cols, long long rows, const f
  * columns moved behind the c_feat descriptor columns.  rows = B*M*S in idx order. */
 int pvn3d_mlp_sa_first(const float *xyz, const float *new_xyz, const float *feat_pm, int ldf,
                        int c_feat, const int *idx, int b, int n, int m, int ns, const float *w,
-                       const float *bias, int k_pad, int n_pad, int relu, int pool, float *out,
+                       const float *bias, int k_pad, int n_pad, int flags, int pool, float *out,
                        int ldo, int col0, pvn3d_stream_t stream);
 /* First layer of an FP module with three_interpolate + concat fused: row (b,j) =
  * [ sum_t nn_w[b,j,t] * known_feat_pm[b, nn_idx[b,j,t], 0:c2] | skip_pm[b, j, 0:c1] | 0.. ] */
 int pvn3d_mlp_fp_first(const float *known_feat_pm, int c2, const int *nn_idx, const float *nn_w,
                        const float *skip_pm, int lds, int c1, int b, int n_unknown, int m_known,
-                       const float *w, const float *bias, int k_pad, int n_pad, int relu, float *out,
+                       const float *w, const float *bias, int k_pad, int n_pad, int flags, float *out,
                        int ldo, int col0, pvn3d_stream_t stream);
 /* weight[p,0:3] = (1/(sqrt(dist2)+1e-8)) / sum  (pointnet2_modules.py:184-186), fp32 IEEE ops */
 int pvn3d_three_nn_weights(const float *dist2, long long rows, float *weight, pvn3d_stream_t stream);

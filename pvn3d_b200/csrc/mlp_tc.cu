@@ -9,7 +9,7 @@
 //
 //   out[p, :] = act( A[p, :] . W^T + bias )            W: BN folded, K-major, TF32-rounded
 //
-// A-operand producers (warps 0-3, one thread per row of the 128-row tile):
+// A-operand producers (warps 4-11, eight lanes per row of the 128-row tile):
 //   DENSE      rows of a point-major activation matrix [P, lda]
 //   SA_GATHER  row (b,j,s): [ feat_pm[b, idx[b,j,s], 0:C] | xyz[b,idx] - new_xyz[b,j] | 0 ... ]
 //              (QueryAndGroup.forward, pointnet2_utils.py:311-321, never materialised; the weight
@@ -17,8 +17,11 @@
 //   FP_INTERP  row (b,j): [ sum_t w_t * known_feat_pm[b, idx_t, 0:C2] | skip[b, j, 0:C1] | 0 ... ]
 //              (three_interpolate + torch.cat of PointnetFPModule.forward, pointnet2_modules.py:188-199)
 // Operands are staged in shared memory in the canonical K-major SWIZZLE_128B layout (32 fp32 = 128 B
-// per row per stage), one elected thread of warp 4 issues tcgen05.mma (M=128, N<=256, K=8 per
-// instruction) and releases stages with tcgen05.commit; the epilogue warps read the accumulator with
+// per row per stage; weights and pre-rounded activations arrive by cp.async), one elected thread of
+// warp 12 issues tcgen05.mma (M=128, N<=256, K=8 per instruction) into one of two TMEM accumulators
+// and releases stages with tcgen05.commit; the kernel is persistent (one CTA per SM, tiles strided),
+// so staging of tile j+1 and the epilogue of tile j-1 overlap the MMAs of tile j.  The epilogue warps
+// (0-3) read the accumulator with
 // tcgen05.ld (32x32b), add the folded-BN bias, apply ReLU and either store the point-major row or
 // reduce over the nsample rows of each centre with a transposing shuffle butterfly (max-pool) and
 // store one 128-byte line per centre.
@@ -31,8 +34,10 @@ namespace pvn3d {
 namespace {
 
 constexpr int kMlpBM = 128;
-constexpr int kMlpThreads = 160;  // warps 0-3: producers + epilogue; warp 4: TMEM owner + MMA issuer
-constexpr int kMlpMaxStages = 4;
+constexpr int kMlpEpiWarps = 4;  // warps 0-3: epilogue (warp w owns TMEM lanes 32w..32w+31)
+constexpr int kMlpProWarps = 8;  // warps 4-11: two producer groups of 128 threads, alternate K chunks
+constexpr int kMlpThreads = (kMlpEpiWarps + kMlpProWarps + 1) * 32;  // warp 12: TMEM owner + MMA issuer
+constexpr int kMlpMaxStages = 6;
 
 enum : int { PRO_DENSE = 0, PRO_SA_GATHER = 1, PRO_FP_INTERP = 2 };
 enum : int { EPI_STORE = 0, EPI_MAXPOOL = 1 };
@@ -44,13 +49,14 @@ struct MlpArgs {
   long long rows;     // P
   int k_pad;          // multiple of 32
   int n_pad;          // multiple of 16
-  int bn;             // columns per CTA (multiple of 16, <= 256)
+  int bn;             // columns per tile (multiple of 16, <= 256)
   int stages;
-  int tmem_cols;      // power of two >= max(32, bn)
+  int tmem_cols;      // power of two >= max(32, bn); two accumulators are allocated
   // DENSE
   const float *a;
   int lda;
   int a_cols;  // valid columns of a (multiple of 4); the rest of k_pad reads as zero
+  int a_tf32;  // a is already TF32-rounded and 16-byte aligned: copied with cp.async, no registers
   // SA_GATHER
   const float *xyz, *new_xyz, *feat;
   const int *idx;
@@ -62,7 +68,8 @@ struct MlpArgs {
   // epilogue
   float *out;
   int ldo, col0, relu;
-  int pool;  // nsample of the max-pool epilogue (8, 16 or 32)
+  int round_out;  // store TF32-rounded values (the next layer then takes them with a_tf32)
+  int pool;       // nsample of the max-pool epilogue (8, 16 or 32)
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
@@ -89,6 +96,15 @@ __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c,
 }
 __device__ __forceinline__ float4 ldg128(const float *p) {
   return __ldg(reinterpret_cast<const float4 *>(p));
+}
+// 16-byte asynchronous copy global -> shared (LDGSTS, L2 only); src_bytes = 0 writes zeros
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, unsigned src_bytes = 16u) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+// the mbarrier gets one (pre-counted) arrival when all cp.async issued so far by this thread landed
+__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                           uint32_t idesc, uint32_t accumulate) {
@@ -161,125 +177,157 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int c) {
   return static_cast<uint32_t>(r) * 128u + (static_cast<uint32_t>(c ^ (r & 7)) << 4);
 }
 
-// ---- A-operand row sources -------------------------------------------------------------------------
-struct RowSrc {
-  // DENSE / generic
-  const float *row;  // start of this row (DENSE: a + p*lda; SA: feature row; FP: skip row)
-  bool live;
-  // SA
-  float dx, dy, dz;
-  // FP
-  const float *k1, *k2, *k3;
-  float w1, w2, w3;
+// ---- A-operand producers ---------------------------------------------------------------------------
+// A producer group is 128 threads = 4 warps; warp pw stages rows 32pw..32pw+31 of the 128-row tile.
+// Inside a warp, 8 consecutive lanes share a row (lane & 7 = the 16-byte chunk of the 128-byte K
+// slice), so one warp-wide LDG.128 reads four full 128-byte lines and one STS.128 fills four swizzled
+// rows without bank conflicts; the 32 rows take 8 passes (row of pass j = 32pw + 4j + lane/8), whose 8
+// loads are all in flight before the first store.
+struct RowState {
+  unsigned live;        // bit j: row of pass j exists (p < rows)
+  const float *row[8];  // DENSE: a + p*lda;  SA: feature row of the grouped point
+  int g1[8], g2[8], g3[8];     // FP: rows of the three neighbours in known_feat (b*m_known + idx)
+  float w1[8], w2[8], w3[8];   // FP: their weights
 };
 
 template <int PRO>
-__device__ __forceinline__ void row_setup(const MlpArgs &a, long long p, RowSrc &s) {
-  s.live = p < a.rows;
-  s.row = nullptr;
-  if (!s.live) return;
-  if (PRO == PRO_DENSE) {
-    s.row = a.a + p * a.lda;
-  } else if (PRO == PRO_SA_GATHER) {
-    const long long per_b = static_cast<long long>(a.m) * a.ns;
-    const int b = static_cast<int>(p / per_b);
-    const int r = static_cast<int>(p - b * per_b);
-    const int j = r / a.ns;
-    const int q = a.idx[p];
-    const float *pt = a.xyz + (static_cast<size_t>(b) * a.n + q) * 3;
-    const float *ct = a.new_xyz + (static_cast<size_t>(b) * a.m + j) * 3;
-    s.dx = __ldg(pt) - __ldg(ct);  // grouped_xyz -= new_xyz (pointnet2_utils.py:314)
-    s.dy = __ldg(pt + 1) - __ldg(ct + 1);
-    s.dz = __ldg(pt + 2) - __ldg(ct + 2);
-    s.row = a.c_feat ? a.feat + (static_cast<size_t>(b) * a.n + q) * a.ldf : nullptr;
-  } else {
-    const int b = static_cast<int>(p / a.n_unknown);
-    const int *ii = a.nn_idx + p * 3;
-    const float *ww = a.nn_w + p * 3;
-    const float *kb = a.known_feat + static_cast<size_t>(b) * a.m_known * a.c2;
-    s.k1 = kb + static_cast<size_t>(ii[0]) * a.c2;
-    s.k2 = kb + static_cast<size_t>(ii[1]) * a.c2;
-    s.k3 = kb + static_cast<size_t>(ii[2]) * a.c2;
-    s.w1 = ww[0];
-    s.w2 = ww[1];
-    s.w3 = ww[2];
-    s.row = a.c1 ? a.skip + p * a.lds : nullptr;
+__device__ __forceinline__ void rows_setup(const MlpArgs &a, long long p_first, RowState &s) {
+  s.live = 0u;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const long long p = p_first + 4 * j;
+    const bool live = p < a.rows;
+    if (live) s.live |= 1u << j;
+    const long long pc = live ? p : 0;
+    if (PRO == PRO_DENSE) {
+      s.row[j] = a.a + pc * a.lda;
+    } else if (PRO == PRO_SA_GATHER) {
+      const long long per_b = static_cast<long long>(a.m) * a.ns;
+      const long long b = pc / per_b;
+      const int q = __ldg(a.idx + pc);
+      s.row[j] = a.feat + (static_cast<size_t>(b) * a.n + q) * a.ldf;  // never read when c_feat == 0
+    } else {
+      const long long b = pc / a.n_unknown;
+      const int base = static_cast<int>(b) * a.m_known;
+      s.g1[j] = base + __ldg(a.nn_idx + pc * 3 + 0);
+      s.g2[j] = base + __ldg(a.nn_idx + pc * 3 + 1);
+      s.g3[j] = base + __ldg(a.nn_idx + pc * 3 + 2);
+      s.w1[j] = __ldg(a.nn_w + pc * 3 + 0);
+      s.w2[j] = __ldg(a.nn_w + pc * 3 + 1);
+      s.w3[j] = __ldg(a.nn_w + pc * 3 + 2);
+    }
   }
 }
 
-// element k of the logical A row (slow path: chunks that straddle a segment boundary / unaligned rows)
+// element k of logical row p (slow path: chunks that straddle a segment boundary / unaligned rows)
 template <int PRO>
-__device__ __forceinline__ float row_elem(const MlpArgs &a, const RowSrc &s, int k) {
-  if (PRO == PRO_DENSE) return k < a.a_cols ? __ldg(s.row + k) : 0.f;
+__device__ __forceinline__ float row_elem(const MlpArgs &a, const RowState &s, int j, long long p, int k) {
+  if (PRO == PRO_DENSE) return k < a.a_cols ? __ldg(s.row[j] + k) : 0.f;
   if (PRO == PRO_SA_GATHER) {
-    if (k < a.c_feat) return __ldg(s.row + k);
+    if (k < a.c_feat) return __ldg(s.row[j] + k);
     const int d = k - a.c_feat;
-    return d == 0 ? s.dx : d == 1 ? s.dy : d == 2 ? s.dz : 0.f;
+    if (d > 2) return 0.f;
+    const long long per_b = static_cast<long long>(a.m) * a.ns;
+    const long long b = p / per_b;
+    const int ctr = static_cast<int>((p - b * per_b) / a.ns);
+    const int q = __ldg(a.idx + p);
+    // grouped_xyz -= new_xyz (pointnet2_utils.py:314)
+    return __ldg(a.xyz + (static_cast<size_t>(b) * a.n + q) * 3 + d) -
+           __ldg(a.new_xyz + (static_cast<size_t>(b) * a.m + ctr) * 3 + d);
   }
-  if (k < a.c2)
-    return __fmaf_rn(__ldg(s.k3 + k), s.w3, __fmaf_rn(__ldg(s.k1 + k), s.w1, __fmul_rn(__ldg(s.k2 + k), s.w2)));
+  if (k < a.c2) {
+    const float *kf = a.known_feat + k;
+    return __fmaf_rn(__ldg(kf + static_cast<size_t>(s.g3[j]) * a.c2), s.w3[j],
+                     __fmaf_rn(__ldg(kf + static_cast<size_t>(s.g1[j]) * a.c2), s.w1[j],
+                               __fmul_rn(__ldg(kf + static_cast<size_t>(s.g2[j]) * a.c2), s.w2[j])));
+  }
   const int d = k - a.c2;
-  return d < a.c1 ? __ldg(s.row + d) : 0.f;
+  return d < a.c1 ? __ldg(a.skip + p * a.lds + d) : 0.f;
 }
 
-// stage the 32 floats [k0, k0+32) of one row into the swizzled A tile
+__device__ __forceinline__ void sts_tf32(uint32_t addr, const float4 &v) {
+  sts128(addr, to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+}
+
+// stage columns [k0 + 4*sub, +4) of this thread's 8 rows into the swizzled A tile at `sa`
 template <int PRO>
-__device__ __forceinline__ void stage_a_row(const MlpArgs &a, const RowSrc &s, int r, int k0,
-                                            uint32_t sa, bool vec_ok) {
-  if (!s.live) {
+__device__ __forceinline__ void stage_a_chunk(const MlpArgs &a, const RowState &s, long long p_first,
+                                              int r_first, int sub, int k0, uint32_t sa, bool vec_ok) {
+  const int k = k0 + 4 * sub;
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (PRO == PRO_DENSE || PRO == PRO_SA_GATHER) {
+    const int seg = PRO == PRO_DENSE ? a.a_cols : a.c_feat;        // vector-loadable prefix of the row
+    const int end = PRO == PRO_DENSE ? a.a_cols : a.c_feat + 3;    // logical row length
+    if (vec_ok && k + 4 <= seg) {
+      float4 v[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) sts128(sa + sw128_off(r, c), 0.f, 0.f, 0.f, 0.f);
-    return;
-  }
-  // fast path: the whole 128-byte chunk comes from one 16-byte-aligned segment
-  if (PRO == PRO_DENSE && vec_ok && k0 + 32 <= a.a_cols) {
-    float4 v[8];
+      for (int j = 0; j < 8; ++j) v[j] = (s.live >> j) & 1u ? ldg128(s.row[j] + k) : zero;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) v[c] = ldg128(s.row + k0 + c * 4);
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-      sts128(sa + sw128_off(r, c), to_tf32(v[c].x), to_tf32(v[c].y), to_tf32(v[c].z), to_tf32(v[c].w));
-    return;
-  }
-  if (PRO == PRO_SA_GATHER && vec_ok && k0 + 32 <= a.c_feat) {
-    float4 v[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) v[c] = ldg128(s.row + k0 + c * 4);
-#pragma unroll
-    for (int c = 0; c < 8; ++c)
-      sts128(sa + sw128_off(r, c), to_tf32(v[c].x), to_tf32(v[c].y), to_tf32(v[c].z), to_tf32(v[c].w));
-    return;
-  }
-  if (PRO == PRO_FP_INTERP && vec_ok && k0 + 32 <= a.c2) {
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float4 p1 = ldg128(s.k1 + k0 + c * 4), p2 = ldg128(s.k2 + k0 + c * 4),
-                   p3 = ldg128(s.k3 + k0 + c * 4);
-      // same contraction as three_interpolate (pn2_ops.cu): fma(p3,w3, fma(p1,w1, p2*w2))
-      const float x = __fmaf_rn(p3.x, s.w3, __fmaf_rn(p1.x, s.w1, __fmul_rn(p2.x, s.w2)));
-      const float y = __fmaf_rn(p3.y, s.w3, __fmaf_rn(p1.y, s.w1, __fmul_rn(p2.y, s.w2)));
-      const float z = __fmaf_rn(p3.z, s.w3, __fmaf_rn(p1.z, s.w1, __fmul_rn(p2.z, s.w2)));
-      const float w = __fmaf_rn(p3.w, s.w3, __fmaf_rn(p1.w, s.w1, __fmul_rn(p2.w, s.w2)));
-      sts128(sa + sw128_off(r, c), to_tf32(x), to_tf32(y), to_tf32(z), to_tf32(w));
+      for (int j = 0; j < 8; ++j) sts_tf32(sa + sw128_off(r_first + 4 * j, sub), v[j]);
+      return;
     }
-    return;
-  }
-  if (PRO == PRO_FP_INTERP && vec_ok && k0 >= a.c2 && k0 - a.c2 + 32 <= a.c1 &&
-      ((reinterpret_cast<uintptr_t>(s.row) & 15u) == 0)) {
-    const float *src = s.row + (k0 - a.c2);
+    if (k >= end) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float4 v = ldg128(src + c * 4);
-      sts128(sa + sw128_off(r, c), to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+      for (int j = 0; j < 8; ++j) sts128(sa + sw128_off(r_first + 4 * j, sub), 0.f, 0.f, 0.f, 0.f);
+      return;
     }
-    return;
-  }
-  // generic path
+  } else {
+    if (vec_ok && k + 4 <= a.c2) {
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const int k = k0 + c * 4;
-    sts128(sa + sw128_off(r, c), to_tf32(row_elem<PRO>(a, s, k)), to_tf32(row_elem<PRO>(a, s, k + 1)),
-           to_tf32(row_elem<PRO>(a, s, k + 2)), to_tf32(row_elem<PRO>(a, s, k + 3)));
+      for (int h = 0; h < 2; ++h) {  // two halves: 12 LDG.128 in flight each
+        float4 p1[4], p2[4], p3[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = h * 4 + jj;
+          const float *kf = a.known_feat + k;
+          p1[jj] = ldg128(kf + static_cast<size_t>(s.g1[j]) * a.c2);
+          p2[jj] = ldg128(kf + static_cast<size_t>(s.g2[j]) * a.c2);
+          p3[jj] = ldg128(kf + static_cast<size_t>(s.g3[j]) * a.c2);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = h * 4 + jj;
+          // same contraction as three_interpolate (pn2_ops.cu): fma(p3,w3, fma(p1,w1, p2*w2))
+          float4 v;
+          v.x = __fmaf_rn(p3[jj].x, s.w3[j], __fmaf_rn(p1[jj].x, s.w1[j], __fmul_rn(p2[jj].x, s.w2[j])));
+          v.y = __fmaf_rn(p3[jj].y, s.w3[j], __fmaf_rn(p1[jj].y, s.w1[j], __fmul_rn(p2[jj].y, s.w2[j])));
+          v.z = __fmaf_rn(p3[jj].z, s.w3[j], __fmaf_rn(p1[jj].z, s.w1[j], __fmul_rn(p2[jj].z, s.w2[j])));
+          v.w = __fmaf_rn(p3[jj].w, s.w3[j], __fmaf_rn(p1[jj].w, s.w1[j], __fmul_rn(p2[jj].w, s.w2[j])));
+          if (!((s.live >> j) & 1u)) v = zero;
+          sts_tf32(sa + sw128_off(r_first + 4 * j, sub), v);
+        }
+      }
+      return;
+    }
+    const bool skip_vec = (a.c2 % 4 == 0) && (a.lds % 4 == 0) &&
+                          ((reinterpret_cast<uintptr_t>(a.skip) & 15u) == 0);
+    if (skip_vec && k >= a.c2 && k - a.c2 + 4 <= a.c1) {
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        v[j] = (s.live >> j) & 1u ? ldg128(a.skip + (p_first + 4 * j) * a.lds + (k - a.c2)) : zero;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sts_tf32(sa + sw128_off(r_first + 4 * j, sub), v[j]);
+      return;
+    }
+    if (k >= a.c2 + a.c1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sts128(sa + sw128_off(r_first + 4 * j, sub), 0.f, 0.f, 0.f, 0.f);
+      return;
+    }
+  }
+  // generic path: element by element
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float4 v = zero;
+    if ((s.live >> j) & 1u) {
+      const long long p = p_first + 4 * j;
+      v.x = row_elem<PRO>(a, s, j, p, k);
+      v.y = row_elem<PRO>(a, s, j, p, k + 1);
+      v.z = row_elem<PRO>(a, s, j, p, k + 2);
+      v.w = row_elem<PRO>(a, s, j, p, k + 3);
+    }
+    sts_tf32(sa + sw128_off(r_first + 4 * j, sub), v);
   }
 }
 
@@ -327,44 +375,52 @@ __device__ __forceinline__ void warp_colmax_8(float (&v)[32], unsigned lane) {
 }
 
 struct MlpSmemCtl {
-  uint64_t full[kMlpMaxStages];
-  uint64_t empty[kMlpMaxStages];
-  uint64_t acc_full;
+  uint64_t full[kMlpMaxStages];   // 256 arrivals: every producer thread of the filling group, twice
+  uint64_t empty[kMlpMaxStages];  // 1 arrival: tcgen05.commit of the MMAs that read the stage
+  uint64_t acc_full[2];           // 1 arrival: tcgen05.commit after a tile's last MMA
+  uint64_t acc_empty[2];          // 128 arrivals: the epilogue threads, once they have read it
   uint32_t tmem_base;
 };
 
+// Persistent, warp-specialised: CTA c works on tiles c, c+grid, ... (tile = 128 rows x bn columns).
+//   producers  fill a ring of K-chunk stages (A: 128 rows x 128 B, B: bn rows x 128 B), running ahead
+//              of the tensor core across tile boundaries;
+//   warp 12    issues the MMAs of tile j into accumulator j&1 of TMEM;
+//   epilogue   drains accumulator j&1 while the MMAs of tile j+1 fill the other one.
 template <int PRO, int EPI>
-__global__ void __launch_bounds__(kMlpThreads, 1) mlp_layer_kernel(MlpArgs a) {
+__global__ void __launch_bounds__(kMlpThreads, 1) mlp_layer_kernel(const __grid_constant__ MlpArgs a) {
   extern __shared__ unsigned char mlp_smem_raw[];
   __shared__ MlpSmemCtl ctl;
   // 1024-byte aligned operand ring (SWIZZLE_128B atoms are 8 rows x 128 B)
   const uint32_t raw = smem_u32(mlp_smem_raw);
   const uint32_t ring = (raw + 1023u) & ~1023u;
   const uint32_t a_bytes = kMlpBM * 128u;
-  const uint32_t b_bytes = static_cast<uint32_t>(a.bn) * 128u;
-  const uint32_t stage_bytes = a_bytes + ((b_bytes + 1023u) & ~1023u);
+  const uint32_t stage_bytes = a_bytes + ((static_cast<uint32_t>(a.bn) * 128u + 1023u) & ~1023u);
 
   const int t = threadIdx.x;
   const unsigned warp = t >> 5, lane = t & 31u;
-  const long long p0 = static_cast<long long>(blockIdx.x) * kMlpBM;
-  const int n0 = blockIdx.y * a.bn;
-  const int bn = min(a.bn, a.n_pad - n0);  // this CTA's columns (multiple of 16)
   const int kc_total = a.k_pad / 32;
   const int S = a.stages;
+  const long long row_tiles = (a.rows + kMlpBM - 1) / kMlpBM;
+  const int n_blocks = (a.n_pad + a.bn - 1) / a.bn;
+  const long long total_tiles = row_tiles * n_blocks;
 
-  if (warp == 4) {
+  if (warp == kMlpEpiWarps + kMlpProWarps) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
-        mbar_init(&ctl.full[s], 128);
+        mbar_init(&ctl.full[s], 256);
         mbar_init(&ctl.empty[s], 1);
       }
-      mbar_init(&ctl.acc_full, 1);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&ctl.acc_full[b], 1);
+        mbar_init(&ctl.acc_empty[b], 128);
+      }
       mbar_fence_init();
     }
     __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(&ctl.tmem_base)),
-                 "r"(static_cast<uint32_t>(a.tmem_cols))
+                 "r"(static_cast<uint32_t>(2 * a.tmem_cols))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -373,129 +429,181 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_layer_kernel(MlpArgs a) {
   tc_fence_after();
   const uint32_t tmem = ctl.tmem_base;
 
-  if (warp < 4) {
-    // ================= producers: thread t stages row t of the A tile, all share the B tile =========
-    RowSrc src;
-    row_setup<PRO>(a, p0 + t, src);
+  if (warp >= kMlpEpiWarps && warp < kMlpEpiWarps + kMlpProWarps) {
+    // ================= producers ======================================================================
+    const int pt = (t - kMlpEpiWarps * 32) & 127;          // thread inside the group
+    const unsigned grp = (warp - kMlpEpiWarps) >> 2;       // group 0 / 1 takes even / odd chunks
+    const int pw = pt >> 5, sub = static_cast<int>(lane & 7u), rg = static_cast<int>(lane >> 3);
+    const int r_first = 32 * pw + rg;
     bool vec_ok = true;
     if (PRO == PRO_DENSE) vec_ok = (a.lda % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.a) & 15u) == 0);
     if (PRO == PRO_SA_GATHER)
       vec_ok = a.c_feat > 0 && (a.ldf % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.feat) & 15u) == 0);
     if (PRO == PRO_FP_INTERP)
       vec_ok = (a.c2 % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.known_feat) & 15u) == 0);
-    for (int kc = 0; kc < kc_total; ++kc) {
-      const int s = kc % S;
-      if (kc >= S) mbar_wait(&ctl.empty[s], static_cast<unsigned>((kc / S - 1) & 1));
-      const uint32_t sa = ring + static_cast<uint32_t>(s) * stage_bytes;
-      const uint32_t sb = sa + a_bytes;
-      stage_a_row<PRO>(a, src, t, kc * 32, sa, vec_ok);
-      // weights: rows n0..n0+bn of W, columns kc*32..+32 (already TF32-rounded and zero-padded)
-      for (int i = t; i < bn * 8; i += 128) {
-        const int n = i >> 3, c = i & 7;
-        const float4 v = ldg128(a.w + static_cast<size_t>(n0 + n) * a.k_pad + kc * 32 + c * 4);
-        sts128(sb + sw128_off(n, c), v.x, v.y, v.z, v.w);
-      }
-      fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor-core (async) proxy
-      mbar_arrive(&ctl.full[s]);
-    }
-
-    // ================= epilogue: warp w owns TMEM lanes 32w..32w+31 = rows p0+32w.. ==================
-    mbar_wait(&ctl.acc_full, 0);
-    tc_fence_after();
-    const long long prow = p0 + warp * 32 + lane;
-    const uint32_t lane_addr = tmem + ((warp * 32u) << 16);
-    for (int c0 = 0; c0 < bn; c0 += 32) {
-      float v[32];
-      const int cw = min(32, bn - c0);
-      if (cw == 32) tmem_ld32(lane_addr + c0, v);
-      else tmem_ld16(lane_addr + c0, v);
-      if (EPI == EPI_STORE) {
-        if (prow < a.rows) {
-          float *o = a.out + prow * a.ldo + a.col0 + n0 + c0;
+    const bool a_async = PRO == PRO_DENSE && a.a_tf32 && vec_ok;
+    long long it_base = 0;  // number of K chunks staged before this tile (same in every role)
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it_base += kc_total) {
+      if (kc_total == 1 && static_cast<unsigned>(it_base & 1) != grp) continue;  // other group's tile
+      const long long rt = tile / n_blocks;
+      const int nb = static_cast<int>(tile - rt * n_blocks);
+      const long long p0 = rt * kMlpBM;
+      const int n0 = nb * a.bn;
+      const int bn = min(a.bn, a.n_pad - n0);
+      const long long p_first = p0 + r_first;
+      RowState rs;
+      rows_setup<PRO>(a, p_first, rs);
+      for (int kc = 0; kc < kc_total; ++kc) {
+        const long long it = it_base + kc;
+        if (static_cast<unsigned>(it & 1) != grp) continue;
+        const int s = static_cast<int>(it % S);
+        mbar_wait(&ctl.empty[s], static_cast<unsigned>(((it / S) & 1) ^ 1));
+        const uint32_t sa = ring + static_cast<uint32_t>(s) * stage_bytes;
+        const uint32_t sb = sa + a_bytes;
+        // weights: rows n0..n0+bn of W, columns kc*32..+32 (TF32-rounded, zero-padded): global -> smem
+        for (int i = pt; i < bn * 8; i += 128) {
+          const int n = i >> 3, c = i & 7;
+          cp_async16(sb + sw128_off(n, c), a.w + static_cast<size_t>(n0 + n) * a.k_pad + kc * 32 + c * 4);
+        }
+        if (a_async) {
+          const int k = kc * 32 + 4 * sub;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            if (q * 4 < cw) {
+          for (int j = 0; j < 8; ++j)
+            cp_async16(sa + sw128_off(r_first + 4 * j, sub), rs.row[j] + (k < a.a_cols ? k : 0),
+                       (((rs.live >> j) & 1u) && k < a.a_cols) ? 16u : 0u);
+          cp_async_arrive_noinc(&ctl.full[s]);
+        } else {
+          cp_async_arrive_noinc(&ctl.full[s]);
+          stage_a_chunk<PRO>(a, rs, p_first, r_first, sub, kc * 32, sa, vec_ok);
+          fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor-core (async) proxy
+        }
+        mbar_arrive(&ctl.full[s]);
+      }
+    }
+  } else if (warp < kMlpEpiWarps) {
+    // ================= epilogue: warp w owns TMEM lanes 32w..32w+31 = rows p0+32w.. ==================
+    long long j = 0;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
+      const long long rt = tile / n_blocks;
+      const int nb = static_cast<int>(tile - rt * n_blocks);
+      const long long p0 = rt * kMlpBM;
+      const int n0 = nb * a.bn;
+      const int bn = min(a.bn, a.n_pad - n0);
+      const unsigned buf = static_cast<unsigned>(j & 1);
+      mbar_wait(&ctl.acc_full[buf], static_cast<unsigned>((j >> 1) & 1));
+      tc_fence_after();
+      const long long prow = p0 + warp * 32 + lane;
+      const uint32_t lane_addr = tmem + buf * static_cast<uint32_t>(a.tmem_cols) + ((warp * 32u) << 16);
+      for (int c0 = 0; c0 < bn; c0 += 32) {
+        float v[32];
+        const int cw = min(32, bn - c0);
+        if (cw == 32) tmem_ld32(lane_addr + c0, v);
+        else tmem_ld16(lane_addr + c0, v);
+        if (EPI == EPI_STORE) {
+          if (prow < a.rows) {
+            float *o = a.out + prow * a.ldo + a.col0 + n0 + c0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              if (q * 4 < cw) {
+                const float4 bq = ldg128(a.bias + n0 + c0 + q * 4);
+                float4 r;
+                r.x = v[q * 4 + 0] + bq.x;
+                r.y = v[q * 4 + 1] + bq.y;
+                r.z = v[q * 4 + 2] + bq.z;
+                r.w = v[q * 4 + 3] + bq.w;
+                if (a.relu) {
+                  r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
+                }
+                if (a.round_out) {
+                  r.x = to_tf32(r.x); r.y = to_tf32(r.y); r.z = to_tf32(r.z); r.w = to_tf32(r.w);
+                }
+                *reinterpret_cast<float4 *>(o + q * 4) = r;
+              }
+            }
+          }
+        } else {
+          // max over the `pool` rows of each centre; rows past the end contribute -inf
+          if (prow >= a.rows) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = -__int_as_float(0x7f800000);
+          }
+          const long long grow0 = (p0 + warp * 32) / a.pool;  // first pooled row of this warp
+          if (a.pool == 32) {
+            warp_colmax_32(v, lane);
+            const int col = static_cast<int>(lane);
+            if (col < cw && p0 + warp * 32 < a.rows) {
+              float r = v[0] + __ldg(a.bias + n0 + c0 + col);
+              if (a.relu) r = fmaxf(r, 0.f);
+              a.out[grow0 * a.ldo + a.col0 + n0 + c0 + col] = r;
+            }
+          } else if (a.pool == 16) {
+            warp_colmax_16(v, lane);
+            const int g = lane >> 4, col = static_cast<int>(lane & 15u) * 2;
+            if (col < cw && p0 + warp * 32 + g * 16 < a.rows) {
+              float2 r;
+              r.x = v[0] + __ldg(a.bias + n0 + c0 + col);
+              r.y = v[1] + __ldg(a.bias + n0 + c0 + col + 1);
+              if (a.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); }
+              *reinterpret_cast<float2 *>(a.out + (grow0 + g) * a.ldo + a.col0 + n0 + c0 + col) = r;
+            }
+          } else {  // pool == 8
+            warp_colmax_8(v, lane);
+            const int g = lane >> 3, col = static_cast<int>(lane & 7u) * 4;
+            if (col < cw && p0 + warp * 32 + g * 8 < a.rows) {
               float4 r;
-              r.x = v[q * 4 + 0] + __ldg(a.bias + n0 + c0 + q * 4 + 0);
-              r.y = v[q * 4 + 1] + __ldg(a.bias + n0 + c0 + q * 4 + 1);
-              r.z = v[q * 4 + 2] + __ldg(a.bias + n0 + c0 + q * 4 + 2);
-              r.w = v[q * 4 + 3] + __ldg(a.bias + n0 + c0 + q * 4 + 3);
+              r.x = v[0] + __ldg(a.bias + n0 + c0 + col);
+              r.y = v[1] + __ldg(a.bias + n0 + c0 + col + 1);
+              r.z = v[2] + __ldg(a.bias + n0 + c0 + col + 2);
+              r.w = v[3] + __ldg(a.bias + n0 + c0 + col + 3);
               if (a.relu) {
                 r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
               }
-              *reinterpret_cast<float4 *>(o + q * 4) = r;
+              *reinterpret_cast<float4 *>(a.out + (grow0 + g) * a.ldo + a.col0 + n0 + c0 + col) = r;
             }
-          }
-        }
-      } else {
-        // max over the `pool` rows of each centre; rows past the end contribute -inf
-        if (prow >= a.rows) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = -__int_as_float(0x7f800000);
-        }
-        const long long grow0 = (p0 + warp * 32) / a.pool;  // first pooled row of this warp
-        if (a.pool == 32) {
-          warp_colmax_32(v, lane);
-          const int col = static_cast<int>(lane);
-          if (col < cw && p0 + warp * 32 < a.rows) {
-            float r = v[0] + __ldg(a.bias + n0 + c0 + col);
-            if (a.relu) r = fmaxf(r, 0.f);
-            a.out[grow0 * a.ldo + a.col0 + n0 + c0 + col] = r;
-          }
-        } else if (a.pool == 16) {
-          warp_colmax_16(v, lane);
-          const int g = lane >> 4, col = static_cast<int>(lane & 15u) * 2;
-          if (col < cw && p0 + warp * 32 + g * 16 < a.rows) {
-            float2 r;
-            r.x = v[0] + __ldg(a.bias + n0 + c0 + col);
-            r.y = v[1] + __ldg(a.bias + n0 + c0 + col + 1);
-            if (a.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); }
-            *reinterpret_cast<float2 *>(a.out + (grow0 + g) * a.ldo + a.col0 + n0 + c0 + col) = r;
-          }
-        } else {  // pool == 8
-          warp_colmax_8(v, lane);
-          const int g = lane >> 3, col = static_cast<int>(lane & 7u) * 4;
-          if (col < cw && p0 + warp * 32 + g * 8 < a.rows) {
-            float4 r;
-            r.x = v[0] + __ldg(a.bias + n0 + c0 + col);
-            r.y = v[1] + __ldg(a.bias + n0 + c0 + col + 1);
-            r.z = v[2] + __ldg(a.bias + n0 + c0 + col + 2);
-            r.w = v[3] + __ldg(a.bias + n0 + c0 + col + 3);
-            if (a.relu) {
-              r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
-            }
-            *reinterpret_cast<float4 *>(a.out + (grow0 + g) * a.ldo + a.col0 + n0 + c0 + col) = r;
           }
         }
       }
+      tc_fence_before();
+      mbar_arrive(&ctl.acc_empty[buf]);  // accumulator `buf` may be overwritten
     }
-    tc_fence_before();
   } else {
-    // ================= warp 4: MMA issuer =============================================================
-    const uint32_t idesc = instr_desc_tf32(bn);
-    for (int kc = 0; kc < kc_total; ++kc) {
-      const int s = kc % S;
-      mbar_wait(&ctl.full[s], static_cast<unsigned>((kc / S) & 1));
+    // ================= warp 12: MMA issuer =============================================================
+    long long it_base = 0, j = 0;
+    for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it_base += kc_total, ++j) {
+      const long long rt = tile / n_blocks;
+      const int nb = static_cast<int>(tile - rt * n_blocks);
+      const int bn = min(a.bn, a.n_pad - nb * a.bn);
+      const uint32_t idesc = instr_desc_tf32(bn);
+      const unsigned buf = static_cast<unsigned>(j & 1);
+      mbar_wait(&ctl.acc_empty[buf], static_cast<unsigned>(((j >> 1) & 1) ^ 1));
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sa = ring + static_cast<uint32_t>(s) * stage_bytes;
-        const uint64_t adesc = smem_desc_sw128(sa), bdesc = smem_desc_sw128(sa + a_bytes);
+      const uint32_t acc = tmem + buf * static_cast<uint32_t>(a.tmem_cols);
+      for (int kc = 0; kc < kc_total; ++kc) {
+        const long long it = it_base + kc;
+        const int s = static_cast<int>(it % S);
+        mbar_wait(&ctl.full[s], static_cast<unsigned>((it / S) & 1));
+        fence_proxy_async_smem();  // cp.async (generic proxy) data of the stage -> async proxy
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = ring + static_cast<uint32_t>(s) * stage_bytes;
+          const uint64_t adesc = smem_desc_sw128(sa), bdesc = smem_desc_sw128(sa + a_bytes);
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4)  // K = 8 tf32 = 32 bytes per instruction: +2 in 16-byte units
-          umma_tf32(tmem, adesc + static_cast<uint64_t>(k4 * 2), bdesc + static_cast<uint64_t>(k4 * 2),
-                    idesc, (kc > 0 || k4 > 0) ? 1u : 0u);
-        umma_commit(&ctl.empty[s]);  // stage reusable once these MMAs have read it
-        if (kc == kc_total - 1) umma_commit(&ctl.acc_full);
+          for (int k4 = 0; k4 < 4; ++k4)  // K = 8 tf32 = 32 bytes per instruction: +2 in 16-byte units
+            umma_tf32(acc, adesc + static_cast<uint64_t>(k4 * 2), bdesc + static_cast<uint64_t>(k4 * 2),
+                      idesc, (kc > 0 || k4 > 0) ? 1u : 0u);
+          umma_commit(&ctl.empty[s]);  // stage reusable once these MMAs have read it
+          if (kc == kc_total - 1) umma_commit(&ctl.acc_full[buf]);
+        }
+        __syncwarp();
       }
-      __syncwarp();
     }
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kMlpEpiWarps + kMlpProWarps) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem),
-                 "r"(static_cast<uint32_t>(a.tmem_cols))
+                 "r"(static_cast<uint32_t>(2 * a.tmem_cols))
                  : "memory");
   }
 }
@@ -504,7 +612,7 @@ template <int PRO, int EPI>
 int launch_mlp(MlpArgs &a, cudaStream_t st) {
   if (a.rows <= 0) return PVN3D_OK;
   if (a.k_pad <= 0 || a.k_pad % 32 || a.n_pad <= 0 || a.n_pad % 16) return PVN3D_ERR_INVALID_ARG;
-  // columns per CTA: <= 256, multiple of 16, as even a split as possible
+  // columns per tile: <= 256, multiple of 16, as even a split as possible
   const int nblk = ceil_div(a.n_pad, 256);
   a.bn = ((ceil_div(a.n_pad, nblk) + 15) / 16) * 16;
   int tc = 32;
@@ -513,8 +621,7 @@ int launch_mlp(MlpArgs &a, cudaStream_t st) {
   const size_t stage_bytes = kMlpBM * 128 + align_up(static_cast<size_t>(a.bn) * 128, 1024);
   int stages = static_cast<int>((200 * 1024) / stage_bytes);
   if (stages > kMlpMaxStages) stages = kMlpMaxStages;
-  if (stages > a.k_pad / 32) stages = a.k_pad / 32;
-  if (stages < 1) stages = 1;
+  if (stages < 2) stages = 2;
   a.stages = stages;
   const size_t smem = stages * stage_bytes + 1024;
   auto kern = mlp_layer_kernel<PRO, EPI>;
@@ -522,9 +629,9 @@ int launch_mlp(MlpArgs &a, cudaStream_t st) {
   if (once.first_time())
     PVN3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024),
                    "mlp smem attr");
-  const long long tiles = (a.rows + kMlpBM - 1) / kMlpBM;
-  if (tiles > 0x7fffffffll) return PVN3D_ERR_UNSUPPORTED;
-  dim3 grid(static_cast<unsigned>(tiles), ceil_div(a.n_pad, a.bn));
+  const int sms = std::max(1, sm_count());
+  const long long tiles = ((a.rows + kMlpBM - 1) / kMlpBM) * ceil_div(a.n_pad, a.bn);
+  const unsigned grid = static_cast<unsigned>(std::min<long long>(tiles, sms));
   kern<<<grid, kMlpThreads, smem, st>>>(a);
   return check_launch("mlp_layer_kernel");
 }
@@ -563,7 +670,7 @@ __global__ void nn_weights_kernel(const float *__restrict__ dist2, long long row
 using namespace pvn3d;
 
 extern "C" int pvn3d_mlp_dense(const float *a, int lda, int a_cols, long long rows, const float *w,
-                               const float *bias, int k_pad, int n_pad, int relu, int pool,
+                               const float *bias, int k_pad, int n_pad, int flags, int pool,
                                float *out, int ldo, int col0, pvn3d_stream_t stream) {
   if (!a || !w || !bias || !out || lda < a_cols || a_cols < 0 || a_cols % 4 || rows < 0 || ldo % 4 ||
       col0 % 4)
@@ -572,13 +679,15 @@ extern "C" int pvn3d_mlp_dense(const float *a, int lda, int a_cols, long long ro
   MlpArgs m{};
   m.w = w; m.bias = bias; m.rows = rows; m.k_pad = k_pad; m.n_pad = n_pad;
   m.a = a; m.lda = lda; m.a_cols = a_cols;
-  m.out = out; m.ldo = ldo; m.col0 = col0; m.relu = relu;
+  m.out = out; m.ldo = ldo; m.col0 = col0;
+  m.relu = flags & PVN3D_MLP_RELU; m.round_out = (flags & PVN3D_MLP_ROUND_OUT) && !pool;
+  m.a_tf32 = (flags & PVN3D_MLP_A_TF32) ? 1 : 0;
   return dispatch(m, PRO_DENSE, pool, as_stream(stream));
 }
 
 extern "C" int pvn3d_mlp_sa_first(const float *xyz, const float *new_xyz, const float *feat_pm,
                                   int ldf, int c_feat, const int *idx, int b, int n, int m, int ns,
-                                  const float *w, const float *bias, int k_pad, int n_pad, int relu,
+                                  const float *w, const float *bias, int k_pad, int n_pad, int flags,
                                   int pool, float *out, int ldo, int col0, pvn3d_stream_t stream) {
   if (!xyz || !new_xyz || !idx || !w || !bias || !out || b < 0 || n <= 0 || m < 0 || ns <= 0 ||
       c_feat < 0 || (c_feat > 0 && (!feat_pm || ldf < c_feat)) || k_pad < c_feat + 3 || ldo % 4 ||
@@ -589,14 +698,15 @@ extern "C" int pvn3d_mlp_sa_first(const float *xyz, const float *new_xyz, const 
   a.w = w; a.bias = bias; a.rows = static_cast<long long>(b) * m * ns; a.k_pad = k_pad; a.n_pad = n_pad;
   a.xyz = xyz; a.new_xyz = new_xyz; a.feat = feat_pm; a.ldf = ldf; a.c_feat = c_feat; a.idx = idx;
   a.n = n; a.m = m; a.ns = ns;
-  a.out = out; a.ldo = ldo; a.col0 = col0; a.relu = relu;
+  a.out = out; a.ldo = ldo; a.col0 = col0;
+  a.relu = flags & PVN3D_MLP_RELU; a.round_out = (flags & PVN3D_MLP_ROUND_OUT) ? 1 : 0;
   return dispatch(a, PRO_SA_GATHER, pool, as_stream(stream));
 }
 
 extern "C" int pvn3d_mlp_fp_first(const float *known_feat_pm, int c2, const int *nn_idx,
                                   const float *nn_w, const float *skip_pm, int lds, int c1, int b,
                                   int n_unknown, int m_known, const float *w, const float *bias,
-                                  int k_pad, int n_pad, int relu, float *out, int ldo, int col0,
+                                  int k_pad, int n_pad, int flags, float *out, int ldo, int col0,
                                   pvn3d_stream_t stream) {
   if (!known_feat_pm || !nn_idx || !nn_w || !w || !bias || !out || b < 0 || n_unknown < 0 ||
       m_known <= 0 || c2 <= 0 || c1 < 0 || (c1 > 0 && (!skip_pm || lds < c1)) || k_pad < c2 + c1 ||
@@ -606,7 +716,8 @@ extern "C" int pvn3d_mlp_fp_first(const float *known_feat_pm, int c2, const int 
   a.w = w; a.bias = bias; a.rows = static_cast<long long>(b) * n_unknown; a.k_pad = k_pad; a.n_pad = n_pad;
   a.known_feat = known_feat_pm; a.c2 = c2; a.nn_idx = nn_idx; a.nn_w = nn_w; a.skip = skip_pm;
   a.lds = lds; a.c1 = c1; a.n_unknown = n_unknown; a.m_known = m_known;
-  a.out = out; a.ldo = ldo; a.col0 = col0; a.relu = relu;
+  a.out = out; a.ldo = ldo; a.col0 = col0;
+  a.relu = flags & PVN3D_MLP_RELU; a.round_out = (flags & PVN3D_MLP_ROUND_OUT) ? 1 : 0;
   return dispatch(a, PRO_FP_INTERP, 0, as_stream(stream));
 }
 

@@ -62,24 +62,34 @@ class PackedLayer:
         self.bias[:n] = bias
 
 
+MLP_RELU, MLP_ROUND_OUT, MLP_A_TF32 = 1, 2, 4      # include/pvn3d_b200.h PVN3D_MLP_*
+
+
+def _flags(relu, round_out=False, a_tf32=False):
+    return (MLP_RELU if relu else 0) | (MLP_ROUND_OUT if round_out else 0) | (MLP_A_TF32 if a_tf32 else 0)
+
+
 def _stream(dev):
     return torch.cuda.current_stream(dev).cuda_stream
 
 
-def mlp_dense(a2d: torch.Tensor, layer: PackedLayer, relu=True, pool=0, out=None, col0=0):
-    """a2d [rows, lda] point-major activations (all lda columns valid or zero)."""
+def mlp_dense(a2d: torch.Tensor, layer: PackedLayer, relu=True, pool=0, out=None, col0=0, round_out=False,
+              a_tf32=False):
+    """a2d [rows, lda] point-major activations (all lda columns valid or zero).  a_tf32: a2d came out of
+    a layer run with round_out=True (values already TF32) -> asynchronous copy path."""
     lib = _lib.load()
     rows, lda = a2d.shape
     if out is None:
         out = torch.empty((rows // pool if pool else rows, layer.n_pad), dtype=torch.float32, device=a2d.device)
     with torch.cuda.device(a2d.device):
         rc = lib.pvn3d_mlp_dense(ptr(a2d), lda, lda, rows, ptr(layer.w), ptr(layer.bias), layer.k_pad, layer.n_pad,
-                                 1 if relu else 0, pool, ptr(out), out.size(-1), col0, _stream(a2d.device))
+                                 _flags(relu, round_out, a_tf32), pool, ptr(out), out.size(-1), col0, _stream(a2d.device))
     check(rc, "pvn3d_mlp_dense")
     return out
 
 
-def mlp_sa_first(xyz, new_xyz, feat_pm, ldf, c_feat, idx, layer: PackedLayer, relu=True, pool=0, out=None, col0=0):
+def mlp_sa_first(xyz, new_xyz, feat_pm, ldf, c_feat, idx, layer: PackedLayer, relu=True, pool=0, out=None, col0=0,
+                 round_out=False):
     lib = _lib.load()
     b, n = xyz.shape[0], xyz.shape[1]
     m, ns = idx.shape[1], idx.shape[2]
@@ -88,20 +98,20 @@ def mlp_sa_first(xyz, new_xyz, feat_pm, ldf, c_feat, idx, layer: PackedLayer, re
         out = torch.empty((rows // pool if pool else rows, layer.n_pad), dtype=torch.float32, device=xyz.device)
     with torch.cuda.device(xyz.device):
         rc = lib.pvn3d_mlp_sa_first(ptr(xyz), ptr(new_xyz), feat_pm, ldf, c_feat, ptr(idx), b, n, m, ns, ptr(layer.w),
-                                    ptr(layer.bias), layer.k_pad, layer.n_pad, 1 if relu else 0, pool, ptr(out),
+                                    ptr(layer.bias), layer.k_pad, layer.n_pad, _flags(relu, round_out), pool, ptr(out),
                                     out.size(-1), col0, _stream(xyz.device))
     check(rc, "pvn3d_mlp_sa_first")
     return out
 
 
-def mlp_fp_first(known_feat_pm, nn_idx, nn_w, skip_ptr, lds, c1, layer: PackedLayer, relu=True):
+def mlp_fp_first(known_feat_pm, nn_idx, nn_w, skip_ptr, lds, c1, layer: PackedLayer, relu=True, round_out=False):
     lib = _lib.load()
     b, m_known, c2 = known_feat_pm.shape
     n_unknown = nn_idx.shape[1]
     out = torch.empty((b * n_unknown, layer.n_pad), dtype=torch.float32, device=known_feat_pm.device)
     with torch.cuda.device(known_feat_pm.device):
         rc = lib.pvn3d_mlp_fp_first(ptr(known_feat_pm), c2, ptr(nn_idx), ptr(nn_w), skip_ptr, lds, c1, b, n_unknown,
-                                    m_known, ptr(layer.w), ptr(layer.bias), layer.k_pad, layer.n_pad, 1 if relu else 0,
+                                    m_known, ptr(layer.w), ptr(layer.bias), layer.k_pad, layer.n_pad, _flags(relu, round_out),
                                     ptr(out), out.size(-1), 0, _stream(known_feat_pm.device))
     check(rc, "pvn3d_mlp_fp_first")
     return out
@@ -171,10 +181,11 @@ class FusedPointnet2MSG:
             col = 0
             idxs = _ext.ball_query2(new_xyz, x, radii, nsamples)    # one pass over the cloud for both radii
             for (idx, ns, layers) in zip(idxs, nsamples, self.sa[li]):
-                h = mlp_sa_first(x, new_xyz, fptr, ldf, c_feat, idx, layers[0])
+                # intermediates are stored TF32-rounded (what the next layer's operand is anyway)
+                h = mlp_sa_first(x, new_xyz, fptr, ldf, c_feat, idx, layers[0], round_out=True)
                 for mid in layers[1:-1]:
-                    h = mlp_dense(h, mid)
-                mlp_dense(h, layers[-1], pool=ns, out=out_l.view(b * npoint, -1), col0=col)
+                    h = mlp_dense(h, mid, round_out=True, a_tf32=True)
+                mlp_dense(h, layers[-1], pool=ns, out=out_l.view(b * npoint, -1), col0=col, a_tf32=True)
                 col += layers[-1].n
             l_xyz.append(new_xyz)
             feats.append((out_l.data_ptr(), out_l.size(-1), out_l.size(-1)))
@@ -190,9 +201,10 @@ class FusedPointnet2MSG:
                 known_feat = known_feat.view(b, known.size(1), -1)
             sptr, lds, c1 = feats[i]
             layers = self.fp[i]
-            h = mlp_fp_first(known_feat, nn_idx, nn_w, sptr, lds, c1, layers[0])
-            for lyr in layers[1:]:
-                h = mlp_dense(h, lyr)
+            h = mlp_fp_first(known_feat, nn_idx, nn_w, sptr, lds, c1, layers[0], round_out=True)
+            for li2, lyr in enumerate(layers[1:]):
+                last = li2 == len(layers) - 2        # level tables stay full fp32
+                h = mlp_dense(h, lyr, round_out=not last, a_tf32=True)
             l_feat[i] = h.view(b, unknown.size(1), -1)
             feats[i] = (h.data_ptr(), h.size(-1), h.size(-1))
         out_pm = l_feat[0]

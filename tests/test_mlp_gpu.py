@@ -26,7 +26,10 @@ def ref_dense(a, w, b, relu, pool):
 @pytest.mark.parametrize("rows,k,n,relu,pool", [
     (128, 32, 16, False, 0), (300, 64, 64, True, 0), (1000, 96, 128, True, 0), (512, 128, 196, True, 0),
     (512, 256, 384, True, 0), (640, 544, 256, True, 0), (2048, 384, 512, True, 32), (1024, 64, 32, True, 16),
-    (256, 32, 16, False, 8), (131, 48, 80, True, 0)])
+    (256, 32, 16, False, 8), (131, 48, 80, True, 0),
+    # many tiles per persistent CTA (ring and both TMEM accumulators wrap), odd chunk counts, 2 column blocks
+    (64000, 96, 128, True, 0), (70005, 32, 32, True, 0), (40960, 64, 64, True, 16), (9000, 544, 512, True, 0),
+    (38400, 160, 272, True, 32)])
 def test_dense_layer(cuda_dev, rows, k, n, relu, pool):
     g = torch.Generator().manual_seed(rows + k + n)
     a = torch.randn(rows, k, generator=g)
@@ -42,6 +45,30 @@ def test_dense_layer(cuda_dev, rows, k, n, relu, pool):
     assert (out[:, :n] - want).abs().max() <= 2e-5 * max(1.0, want.abs().max())
     if layer.n_pad > n:
         assert out[:, n:].abs().max() == 0           # pad columns are exact zeros for the next layer
+
+
+@pytest.mark.parametrize("rows,k,n1,n2", [(50000, 64, 96, 128), (3000, 256, 384, 512), (20000, 32, 16, 32)])
+def test_chained_layers_take_tf32_activations_asynchronously(cuda_dev, rows, k, n1, n2):
+    """layer 1 stores TF32-rounded activations (ROUND_OUT), layer 2 copies them with cp.async (A_TF32):
+    same numbers as rounding while staging."""
+    g = torch.Generator().manual_seed(rows + k)
+    a = torch.randn(rows, k, generator=g)
+    w1 = torch.randn(n1, k, generator=g) / np.sqrt(k)
+    w2 = torch.randn(n2, n1, generator=g) / np.sqrt(n1)
+    b1, b2 = torch.randn(n1, generator=g), torch.randn(n2, generator=g)
+    l1 = mlp.PackedLayer(w1.to(cuda_dev), b1.to(cuda_dev))
+    l2 = mlp.PackedLayer(w2.to(cuda_dev), b2.to(cuda_dev), l1.n_pad)
+    ad = torch.zeros(rows, (k + 15) // 16 * 16, device=cuda_dev)
+    ad[:, :k] = a.to(cuda_dev)
+    h = mlp.mlp_dense(ad, l1, round_out=True)
+    assert torch.equal(h, mlp.tf32_round(h))
+    h_plain = mlp.mlp_dense(ad, l1)
+    assert torch.equal(h, mlp.tf32_round(h_plain))
+    out = mlp.mlp_dense(h, l2, a_tf32=True)
+    out_sync = mlp.mlp_dense(h_plain, l2)
+    assert torch.equal(out, out_sync)
+    want = ref_dense(h.cpu()[:, :n1], mlp.tf32_round(w2), b2, True, 0)
+    assert (out.cpu()[:, :n2] - want).abs().max() <= 2e-5 * max(1.0, want.abs().max())
 
 
 def test_sa_first_layer_fuses_query_and_group(cuda_dev):
