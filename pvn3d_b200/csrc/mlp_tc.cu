@@ -94,6 +94,11 @@ __device__ __forceinline__ void sts128(uint32_t addr, float a, float b, float c,
   asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
                : "memory");
 }
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ float4 ldg128(const float *p) {
   return __ldg(reinterpret_cast<const float4 *>(p));
 }
@@ -186,28 +191,46 @@ __device__ __forceinline__ uint32_t sw128_off(int r, int c) {
 struct RowState {
   unsigned live;        // bit j: row of pass j exists (p < rows)
   const float *row[8];  // DENSE: a + p*lda;  SA: feature row of the grouped point
+  int qrow[8], crow[8];        // SA: row of the grouped point in xyz (b*n + idx), of its centre (b*m + j)
   int g1[8], g2[8], g3[8];     // FP: rows of the three neighbours in known_feat (b*m_known + idx)
   float w1[8], w2[8], w3[8];   // FP: their weights
 };
 
+// rows p_first, p_first+4, ..: batch index and offset inside the batch with ONE 64-bit division
 template <int PRO>
 __device__ __forceinline__ void rows_setup(const MlpArgs &a, long long p_first, RowState &s) {
   s.live = 0u;
+  const unsigned per_b = PRO == PRO_SA_GATHER ? static_cast<unsigned>(a.m) * static_cast<unsigned>(a.ns)
+                                              : static_cast<unsigned>(a.n_unknown);
+  unsigned b0 = 0, rem0 = 0;
+  if (PRO != PRO_DENSE) {
+    const long long pf = p_first < a.rows ? p_first : 0;
+    b0 = static_cast<unsigned>(pf / per_b);
+    rem0 = static_cast<unsigned>(pf - static_cast<long long>(b0) * per_b);
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const long long p = p_first + 4 * j;
     const bool live = p < a.rows;
     if (live) s.live |= 1u << j;
     const long long pc = live ? p : 0;
+    unsigned rem = rem0 + 4u * j, b = b0;
+    if (PRO != PRO_DENSE) {
+      if (rem >= per_b) {
+        const unsigned over = rem / per_b;
+        b += over;
+        rem -= over * per_b;
+      }
+      if (!live) { b = 0; rem = 0; }
+    }
     if (PRO == PRO_DENSE) {
       s.row[j] = a.a + pc * a.lda;
     } else if (PRO == PRO_SA_GATHER) {
-      const long long per_b = static_cast<long long>(a.m) * a.ns;
-      const long long b = pc / per_b;
       const int q = __ldg(a.idx + pc);
-      s.row[j] = a.feat + (static_cast<size_t>(b) * a.n + q) * a.ldf;  // never read when c_feat == 0
+      s.qrow[j] = static_cast<int>(b) * a.n + q;
+      s.crow[j] = static_cast<int>(b) * a.m + static_cast<int>(rem / static_cast<unsigned>(a.ns));
+      s.row[j] = a.feat + static_cast<size_t>(s.qrow[j]) * a.ldf;  // never read when c_feat == 0
     } else {
-      const long long b = pc / a.n_unknown;
       const int base = static_cast<int>(b) * a.m_known;
       s.g1[j] = base + __ldg(a.nn_idx + pc * 3 + 0);
       s.g2[j] = base + __ldg(a.nn_idx + pc * 3 + 1);
@@ -227,13 +250,9 @@ __device__ __forceinline__ float row_elem(const MlpArgs &a, const RowState &s, i
     if (k < a.c_feat) return __ldg(s.row[j] + k);
     const int d = k - a.c_feat;
     if (d > 2) return 0.f;
-    const long long per_b = static_cast<long long>(a.m) * a.ns;
-    const long long b = p / per_b;
-    const int ctr = static_cast<int>((p - b * per_b) / a.ns);
-    const int q = __ldg(a.idx + p);
     // grouped_xyz -= new_xyz (pointnet2_utils.py:314)
-    return __ldg(a.xyz + (static_cast<size_t>(b) * a.n + q) * 3 + d) -
-           __ldg(a.new_xyz + (static_cast<size_t>(b) * a.m + ctr) * 3 + d);
+    return __ldg(a.xyz + static_cast<size_t>(s.qrow[j]) * 3 + d) -
+           __ldg(a.new_xyz + static_cast<size_t>(s.crow[j]) * 3 + d);
   }
   if (k < a.c2) {
     const float *kf = a.known_feat + k;
@@ -493,6 +512,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_layer_kernel(const __grid_
       mbar_wait(&ctl.acc_full[buf], static_cast<unsigned>((j >> 1) & 1));
       tc_fence_after();
       const long long prow = p0 + warp * 32 + lane;
+      const uint32_t stg = ring + static_cast<uint32_t>(S) * stage_bytes + warp * 4096u;  // after the ring
       const uint32_t lane_addr = tmem + buf * static_cast<uint32_t>(a.tmem_cols) + ((warp * 32u) << 16);
       for (int c0 = 0; c0 < bn; c0 += 32) {
         float v[32];
@@ -500,27 +520,40 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_layer_kernel(const __grid_
         if (cw == 32) tmem_ld32(lane_addr + c0, v);
         else tmem_ld16(lane_addr + c0, v);
         if (EPI == EPI_STORE) {
-          if (prow < a.rows) {
-            float *o = a.out + prow * a.ldo + a.col0 + n0 + c0;
+          // bias / ReLU / rounding on the thread's own row, then through a swizzled 4 KB staging tile
+          // so that the global stores are 128-byte row segments (8 lanes per row, 4 rows per STG.128)
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              if (q * 4 < cw) {
-                const float4 bq = ldg128(a.bias + n0 + c0 + q * 4);
-                float4 r;
-                r.x = v[q * 4 + 0] + bq.x;
-                r.y = v[q * 4 + 1] + bq.y;
-                r.z = v[q * 4 + 2] + bq.z;
-                r.w = v[q * 4 + 3] + bq.w;
-                if (a.relu) {
-                  r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
-                }
-                if (a.round_out) {
-                  r.x = to_tf32(r.x); r.y = to_tf32(r.y); r.z = to_tf32(r.z); r.w = to_tf32(r.w);
-                }
-                *reinterpret_cast<float4 *>(o + q * 4) = r;
+          for (int q = 0; q < 8; ++q) {
+            if (q * 4 < cw) {
+              const float4 bq = ldg128(a.bias + n0 + c0 + q * 4);
+              float4 r;
+              r.x = v[q * 4 + 0] + bq.x;
+              r.y = v[q * 4 + 1] + bq.y;
+              r.z = v[q * 4 + 2] + bq.z;
+              r.w = v[q * 4 + 3] + bq.w;
+              if (a.relu) {
+                r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
+              }
+              if (a.round_out) {
+                r.x = to_tf32(r.x); r.y = to_tf32(r.y); r.z = to_tf32(r.z); r.w = to_tf32(r.w);
+              }
+              sts128(stg + lane * 128u + ((static_cast<uint32_t>(q) ^ (lane & 7u)) << 4), r.x, r.y, r.z, r.w);
+            }
+          }
+          __syncwarp();
+          const unsigned chunk = lane & 7u;
+          if (static_cast<int>(chunk) * 4 < cw) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const unsigned row = 4u * i + (lane >> 3);
+              const long long pr = p0 + warp * 32 + row;
+              if (pr < a.rows) {
+                const float4 r = lds128(stg + row * 128u + ((chunk ^ (row & 7u)) << 4));
+                *reinterpret_cast<float4 *>(a.out + pr * a.ldo + a.col0 + n0 + c0 + chunk * 4) = r;
               }
             }
           }
+          __syncwarp();
         } else {
           // max over the `pool` rows of each centre; rows past the end contribute -inf
           if (prow >= a.rows) {
@@ -619,15 +652,15 @@ int launch_mlp(MlpArgs &a, cudaStream_t st) {
   while (tc < a.bn) tc <<= 1;
   a.tmem_cols = tc;
   const size_t stage_bytes = kMlpBM * 128 + align_up(static_cast<size_t>(a.bn) * 128, 1024);
-  int stages = static_cast<int>((200 * 1024) / stage_bytes);
+  int stages = static_cast<int>((208 * 1024) / stage_bytes);
   if (stages > kMlpMaxStages) stages = kMlpMaxStages;
   if (stages < 2) stages = 2;
   a.stages = stages;
-  const size_t smem = stages * stage_bytes + 1024;
+  const size_t smem = stages * stage_bytes + 1024 + kMlpEpiWarps * 4096;  // ring + epilogue staging
   auto kern = mlp_layer_kernel<PRO, EPI>;
   static PerDeviceOnce once;
   if (once.first_time())
-    PVN3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024),
+    PVN3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024),
                    "mlp smem attr");
   const int sms = std::max(1, sm_count());
   const long long tiles = ((a.rows + kMlpBM - 1) / kMlpBM) * ceil_div(a.n_pad, a.bn);
@@ -694,6 +727,9 @@ extern "C" int pvn3d_mlp_sa_first(const float *xyz, const float *new_xyz, const 
       col0 % 4)
     return PVN3D_ERR_INVALID_ARG;
   if (pool && pool != ns) return PVN3D_ERR_INVALID_ARG;
+  if (static_cast<long long>(m) * ns > 0x3fffffffll || static_cast<long long>(b) * n > 0x7fffffffll ||
+      static_cast<long long>(b) * m > 0x7fffffffll)
+    return PVN3D_ERR_UNSUPPORTED;
   MlpArgs a{};
   a.w = w; a.bias = bias; a.rows = static_cast<long long>(b) * m * ns; a.k_pad = k_pad; a.n_pad = n_pad;
   a.xyz = xyz; a.new_xyz = new_xyz; a.feat = feat_pm; a.ldf = ldf; a.c_feat = c_feat; a.idx = idx;
@@ -712,6 +748,8 @@ extern "C" int pvn3d_mlp_fp_first(const float *known_feat_pm, int c2, const int 
       m_known <= 0 || c2 <= 0 || c1 < 0 || (c1 > 0 && (!skip_pm || lds < c1)) || k_pad < c2 + c1 ||
       ldo % 4 || col0 % 4)
     return PVN3D_ERR_INVALID_ARG;
+  if (static_cast<long long>(b) * m_known > 0x7fffffffll || n_unknown > 0x3fffffff)
+    return PVN3D_ERR_UNSUPPORTED;
   MlpArgs a{};
   a.w = w; a.bias = bias; a.rows = static_cast<long long>(b) * n_unknown; a.k_pad = k_pad; a.n_pad = n_pad;
   a.known_feat = known_feat_pm; a.c2 = c2; a.nn_idx = nn_idx; a.nn_w = nn_w; a.skip = skip_pm;
