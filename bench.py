@@ -389,7 +389,7 @@ def roofline_query_group(torch, _ext, dev, B, cloud, peak, peak_kind):
         xyz = new_xyz
     achieved = total_bytes / total_ms / 1e6
     big = max(per, key=lambda p: p["MB"])
-    return {"kernel": "query_group_kernel (fused ball-query+group, both radii of a level per launch: 4 launches of one batch)", "bound": "hbm",
+    return {"kernel": "pvn3d_query_and_group2 = ball_scan_kernel + group_write_kernel (fused ball-query+group, both radii of a level per call: 4 calls of one batch)", "bound": "hbm",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
             "traffic": None, "algorithmic_MB_per_batch": total_bytes / 1e6, "us_per_batch": total_ms * 1e3,
             "largest_launch": big, "per_launch": per}

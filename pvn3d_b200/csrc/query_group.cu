@@ -8,21 +8,24 @@
 // optionally for the TWO radii of a multi-scale-grouping level at once (same centres, same cloud:
 // every squared distance is computed once and compared against both radii).
 //
-// Per CTA (8 warps, CW centres per warp):
-//   phase 1  every 128-point block of the cloud gets a bounding box (and every 8 blocks a super box) in
-//            shared memory; then each warp walks the cloud ON ITS OWN -- no tile staging, no CTA
-//            barriers -- balloting 32 points per step against its CW centres (hits are appended in
-//            index order: the reference's first-nsample rule by construction) and skipping every
-//            block whose box is out of reach of the box of its centres.  Exact pruning: free on
-//            shuffled clouds, removes ~90 % of the scan on raster-ordered ones (the reference's
-//            samplers keep raster order).  The cloud is read through L1/L2 (384 contiguous bytes per
-//            step); the TMA-staged variant of the scan lives on in pn2_ops.cu:ball_query_kernel.
-//   phase 2  descriptors are read POINT-MAJOR (feat_pm[B,N,ldf]).  A warp owns 32 consecutive slots:
-//            cp.async pulls 32 channels of four neighbours per instruction (8 lanes = one fully used
-//            128-byte run) into one of two private shared-memory tiles while the previous tile is
-//            written out as 16-byte stores -- 8 lanes cover one 128-byte line of a channel row, a
-//            warp instruction four rows -- after a 4x4 register transpose.  Every output byte is
-//            written once, every gathered sector is fully used.
+// Two kernels per launch (plus two tiny pre-passes):
+//   pre-pass   bounding box of every 128-point block of the cloud; scan order of the centres (bucketed
+//              by y, so that the CW centres a warp scans for together are neighbours).
+//   scan       (ball_scan_kernel, 8 warps x CW centres per CTA, little shared memory -> 5+ CTAs/SM)
+//              each warp walks the cloud ON ITS OWN -- no tile staging, no CTA barriers -- balloting 32
+//              points per step against its CW centres (hits are appended in index order: the
+//              reference's first-nsample rule by construction) and skipping every block whose box is
+//              out of reach of the box of its centres.  Exact pruning: free on shuffled clouds, removes
+//              ~90 % of the scan on raster-ordered ones (the reference's samplers keep raster order).
+//              The next step's points are loaded while the current ones are tested.  Result: idx[B,M,S]
+//              (the caller's buffer, or stream-ordered scratch when only the grouped tensor is wanted).
+//   group      (group_write_kernel, 1024 consecutive output slots of one scale per CTA, 3 CTAs/SM)
+//              descriptors are read POINT-MAJOR (feat_pm[B,N,ldf]).  A warp owns 32 consecutive slots:
+//              cp.async pulls 32 channels of four neighbours per instruction (8 lanes = one fully used
+//              128-byte run) into one of two private shared-memory tiles while the previous tile is
+//              written out as 16-byte stores -- 8 lanes cover one 128-byte line of a channel row, a
+//              warp instruction four rows -- after a 4x4 register transpose.  Every output byte is
+//              written once, in runs of 4 KB per channel and CTA; every gathered sector is fully used.
 // Algorithmic HBM bytes per launch and scale:
 //   B * [ 12 N + 12 M + 4 C N  (reads)  +  4 M S + 4 (3+C) M S  (writes) ].
 #include "common.cuh"
@@ -32,9 +35,10 @@ namespace {
 
 constexpr int kQgThreads = 256;
 constexpr int kQgWarps = 8;
-constexpr int kQgTile = 1024;      // (sizes the 24 KB box table: 1024 boxes of 6 floats)
-constexpr int kQgMaxSlots = 2048;  // slots (centres x nsample, both scales) per CTA
-constexpr int kQgTrStride = 36;    // floats per row of a per-warp [32 slots][32 channels] tile
+constexpr int kQgMaxBlocks = 1024;  // bounding-box blocks per cloud (24 KB of shared memory at most)
+constexpr int kQgMaxSlots = 2048;   // scan: slots (centres x nsample, both scales) per CTA
+constexpr int kQgGroupSlots = 1024; // group: consecutive output slots of one scale per CTA
+constexpr int kQgTrStride = 36;     // floats per row of a per-warp [32 slots][32 channels] tile
 constexpr int kQgTrFloats = 32 * kQgTrStride;  // one tile; every warp owns two (double buffering)
 static_assert(2 * kQgTrFloats >= 32 * 33, "scalar fallback transposes through the same buffer");
 
@@ -48,15 +52,15 @@ struct QgArgs {
   const float *xyz, *new_xyz, *feat;
   int ldf, n, m, c;
   int blk;  // points per bounding-box block (multiple of 32; at most 896 blocks + their super boxes)
-  const float *boxes;  // [B][nblk + nsup][6] from qg_boxes_kernel
+  const float *boxes;  // [B][nblk][6] from qg_boxes_kernel
+  const int *perm;     // [B][M] centres in scan order (sorted by y) from qg_sort_centres_kernel
   QgScale s[2];
 };
 
-struct QgSmem {
-  static constexpr size_t tile_bytes = 2 * kQgTile * 3 * sizeof(float);                    // 24576
-  static constexpr size_t rows_bytes = kQgMaxSlots * sizeof(int);                          // 8192
+struct QgGroupSmem {
+  static constexpr size_t rows_bytes = kQgGroupSlots * sizeof(int);                        // 4096
   static constexpr size_t tr_bytes = kQgWarps * 2 * kQgTrFloats * sizeof(float);           // 73728
-  static constexpr size_t total = tile_bytes + rows_bytes + tr_bytes;
+  static constexpr size_t total = rows_bytes + tr_bytes;
 };
 
 __device__ __forceinline__ void qg_append(unsigned hits, int &cnt, int &first, int ns, int *row,
@@ -77,34 +81,32 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 // write one scale's slots of this CTA: xyz difference channels + descriptor channels
-__device__ __forceinline__ void qg_write_scale(const QgArgs &a, const QgScale &sc, int b, int jc0,
-                                               int live_centres, const int *rows, float *s_tr) {
+// write the CTA's slots [slot0, slot0 + nslots) of one scale (slot = centre * ns + neighbour):
+// xyz difference channels + descriptor channels.  rows[s] = index of the neighbour in the cloud.
+__device__ __forceinline__ void qg_write_scale(const QgArgs &a, const QgScale &sc, int b, int slot0,
+                                               int nslots, const int *rows, float *s_tr) {
   const int t = threadIdx.x;
   const unsigned lane = lane_id(), warp = t >> 5;
   const int ns = sc.ns, c = a.c;
-  const int nslots = live_centres * ns;
   const size_t plane = static_cast<size_t>(a.m) * ns;
-  const size_t slot_base = static_cast<size_t>(jc0) * ns;
+  const size_t slot_base = static_cast<size_t>(slot0);
   const float *cloud = a.xyz + static_cast<size_t>(b) * a.n * 3;
   float *out_b = sc.out + static_cast<size_t>(b) * (3 + c) * plane + slot_base;
 
   for (int s = t; s < nslots; s += kQgThreads) {
     const int p = rows[s];
-    if (sc.idx) sc.idx[static_cast<size_t>(b) * plane + slot_base + s] = p;
-    if (sc.out) {
-      // grouped_xyz - new_xyz  (pointnet2_utils.py:313-314)
-      const float *ctr = a.new_xyz + (static_cast<size_t>(b) * a.m + jc0 + s / ns) * 3;
-      const float *pt = cloud + static_cast<size_t>(p) * 3;
-      stg_stream(out_b + 0 * plane + s, __ldg(pt + 0) - __ldg(ctr + 0));
-      stg_stream(out_b + 1 * plane + s, __ldg(pt + 1) - __ldg(ctr + 1));
-      stg_stream(out_b + 2 * plane + s, __ldg(pt + 2) - __ldg(ctr + 2));
-    }
+    // grouped_xyz - new_xyz  (pointnet2_utils.py:313-314)
+    const float *ctr = a.new_xyz + (static_cast<size_t>(b) * a.m + (slot0 + s) / ns) * 3;
+    const float *pt = cloud + static_cast<size_t>(p) * 3;
+    stg_stream(out_b + 0 * plane + s, __ldg(pt + 0) - __ldg(ctr + 0));
+    stg_stream(out_b + 1 * plane + s, __ldg(pt + 1) - __ldg(ctr + 1));
+    stg_stream(out_b + 2 * plane + s, __ldg(pt + 2) - __ldg(ctr + 2));
   }
-  if (!sc.out || c == 0) return;
+  if (c == 0) return;
   const float *feat_b = a.feat + static_cast<size_t>(b) * a.n * a.ldf;
   float *out_f = out_b + 3 * plane;
   const bool vec = (c % 4 == 0) && (a.ldf % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.feat) & 15u) == 0) &&
-                   (plane % 4 == 0) && (slot_base % 4 == 0) && (ns % 4 == 0) &&
+                   (plane % 4 == 0) && (slot_base % 4 == 0) && (nslots % 4 == 0) &&
                    ((reinterpret_cast<uintptr_t>(sc.out) & 15u) == 0);
   float *tr = s_tr + warp * (2 * kQgTrFloats);
   const int ngroups = (nslots + 31) / 32;
@@ -145,7 +147,7 @@ __device__ __forceinline__ void qg_write_scale(const QgArgs &a, const QgScale &s
       __syncwarp();
       const int g0 = (static_cast<int>(warp) + (item / nchunks) * kQgWarps) * 32;
       const int c0 = (item % nchunks) * 32;
-      const int glive = min(32, nslots - g0);  // multiple of 4 (ns % 4 == 0)
+      const int glive = min(32, nslots - g0);  // multiple of 4 (nslots % 4 == 0)
       const int quads = min(8, (c - c0) / 4);
       if (4 * m8 < glive) {
 #pragma unroll
@@ -201,8 +203,8 @@ __device__ __forceinline__ void qg_write_scale(const QgArgs &a, const QgScale &s
 }
 
 // Bounding boxes of every block of `blk` consecutive points (one warp per block) -- computed once per
-// cloud, not once per CTA.  Super boxes (8 blocks) are appended by qg_supboxes_kernel.
-__global__ void qg_boxes_kernel(const float *__restrict__ xyz, int n, int blk, int nblk, int nsup,
+// cloud, not once per CTA.
+__global__ void qg_boxes_kernel(const float *__restrict__ xyz, int n, int blk, int nblk,
                                 float *__restrict__ boxes) {
   const int b = blockIdx.y;
   const unsigned lane = lane_id();
@@ -229,7 +231,7 @@ __global__ void qg_boxes_kernel(const float *__restrict__ xyz, int n, int blk, i
     }
   }
   if (lane == 0) {
-    float *o = boxes + (static_cast<size_t>(b) * (nblk + nsup) + g) * 6;
+    float *o = boxes + (static_cast<size_t>(b) * nblk + g) * 6;
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       o[d] = lo[d];
@@ -237,16 +239,70 @@ __global__ void qg_boxes_kernel(const float *__restrict__ xyz, int n, int blk, i
     }
   }
 }
-__global__ void qg_supboxes_kernel(int nblk, int nsup, float *__restrict__ boxes) {
-  const int b = blockIdx.y;
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= nsup * 6) return;
-  float *base = boxes + static_cast<size_t>(b) * (nblk + nsup) * 6;
-  const int sb = e / 6, d = e % 6;
-  float v = base[(sb * 8) * 6 + d];
-  for (int i = 1; i < 8 && sb * 8 + i < nblk; ++i)
-    v = d < 3 ? fminf(v, base[(sb * 8 + i) * 6 + d]) : fmaxf(v, base[(sb * 8 + i) * 6 + d]);
-  base[(nblk + sb) * 6 + d] = v;
+// Scan order of the centres of one cloud: bucketed by y (1024 buckets between the smallest and the
+// largest y; the order inside a bucket is whatever the atomics give).  FPS hands the centres out
+// scattered all over the cloud; the CW centres a warp scans for together must be NEIGHBOURS for the
+// union of their balls to stay as small as one ball (and the blocks of a raster-ordered cloud are
+// thin in y).  ANY order gives the same output, so a counting sort is enough.  One CTA per cloud.
+constexpr int kQgSortMax = 1 << 20;
+constexpr int kQgBuckets = 1024;
+__global__ void __launch_bounds__(1024) qg_sort_centres_kernel(const float *__restrict__ new_xyz, int m,
+                                                               int *__restrict__ perm) {
+  __shared__ int s_cnt[kQgBuckets];
+  __shared__ float s_lo[32], s_hi[32];
+  __shared__ int s_warp[32];
+  const int b = blockIdx.x, t = threadIdx.x;
+  const unsigned lane = lane_id(), warp = t >> 5;
+  const float *ys = new_xyz + static_cast<size_t>(b) * m * 3 + 1;
+  float lo = 3.0e38f, hi = -3.0e38f;
+  for (int i = t; i < m; i += 1024) {
+    const float y = ys[static_cast<size_t>(i) * 3];
+    if (fabsf(y) < 3.0e38f) {  // finite
+      lo = fminf(lo, y);
+      hi = fmaxf(hi, y);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (lane == 0) { s_lo[warp] = lo; s_hi[warp] = hi; }
+  s_cnt[t] = 0;
+  __syncthreads();
+  lo = s_lo[0]; hi = s_hi[0];
+  for (int w = 1; w < 32; ++w) { lo = fminf(lo, s_lo[w]); hi = fmaxf(hi, s_hi[w]); }
+  const float scale = hi > lo ? static_cast<float>(kQgBuckets) / (hi - lo) : 0.f;
+  auto bucket = [&](float y) {
+    if (!(fabsf(y) < 3.0e38f)) return kQgBuckets - 1;  // NaN / inf: last bucket
+    const int k = static_cast<int>((y - lo) * scale);
+    return max(0, min(kQgBuckets - 1, k));
+  };
+  for (int i = t; i < m; i += 1024) atomicAdd(&s_cnt[bucket(ys[static_cast<size_t>(i) * 3])], 1);
+  __syncthreads();
+  // exclusive scan of the 1024 counts (one per thread)
+  const int mine = s_cnt[t];
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (static_cast<int>(lane) >= o) incl += v;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  int base = 0;
+  for (int w = 0; w < static_cast<int>(warp); ++w) base += s_warp[w];
+  __syncthreads();
+  s_cnt[t] = base + incl - mine;  // first output position of bucket t
+  __syncthreads();
+  for (int i = t; i < m; i += 1024) {
+    const int pos = atomicAdd(&s_cnt[bucket(ys[static_cast<size_t>(i) * 3])], 1);
+    perm[static_cast<size_t>(b) * m + pos] = i;
+  }
+}
+__global__ void qg_identity_perm_kernel(int m, int *__restrict__ perm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < m) perm[static_cast<size_t>(blockIdx.y) * m + i] = i;
 }
 
 // squared distance between two axis-aligned boxes (0 when they overlap); b[0..2] = lo, b[3..5] = hi
@@ -258,12 +314,11 @@ __device__ __forceinline__ float qg_box_dist2(const float (&u)[6], const float *
 }
 
 template <int CW, bool DUAL>
-__global__ void __launch_bounds__(kQgThreads, 2) query_group_kernel(QgArgs a) {
+__global__ void __launch_bounds__(kQgThreads, 4) ball_scan_kernel(QgArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float *s_box = reinterpret_cast<float *>(smem_raw);  // [nblk][6] block boxes, then [nsup][6] super boxes
-  int *s_rows = reinterpret_cast<int *>(smem_raw + QgSmem::tile_bytes);
-  float *s_tr = reinterpret_cast<float *>(smem_raw + QgSmem::tile_bytes + QgSmem::rows_bytes);
-  __shared__ int s_perm[32];  // scan slot -> local centre, sorted by y
+  int *s_rows = reinterpret_cast<int *>(smem_raw);                                      // [kQgMaxSlots]
+  float *s_box = reinterpret_cast<float *>(smem_raw + kQgMaxSlots * sizeof(int));       // [nblk][6]
+  __shared__ int s_cent[32];  // local centre (scan slot) -> centre index in the cloud
 
   constexpr int TJ = kQgWarps * CW;
   const int b = blockIdx.y;
@@ -281,37 +336,17 @@ __global__ void __launch_bounds__(kQgThreads, 2) query_group_kernel(QgArgs a) {
   int *rows_a = s_rows;             // [TJ][nsa]
   int *rows_b = s_rows + TJ * nsa;  // [TJ][nsb]
 
-  // ---- bounding boxes of the cloud's blocks (a.blk points each) and of groups of 8 blocks -----------
-  const int blk = a.blk, nblk = (a.n + blk - 1) / blk, nsup = (nblk + 7) / 8;
-  float *s_sup = s_box + nblk * 6;
+  // ---- bounding boxes of the cloud's blocks (a.blk points each) -------------------------------------
+  const int blk = a.blk, nblk = (a.n + blk - 1) / blk;
   {
-    const float *src = a.boxes + static_cast<size_t>(b) * (nblk + nsup) * 6;
-    for (int e = threadIdx.x; e < (nblk + nsup) * 6; e += kQgThreads) s_box[e] = __ldg(src + e);
+    const float *src = a.boxes + static_cast<size_t>(b) * nblk * 6;
+    for (int e = threadIdx.x; e < nblk * 6; e += kQgThreads) s_box[e] = __ldg(src + e);
   }
-  // The CTA's centres are dealt to the warps in order of their y coordinate, so that the CW centres a
-  // warp scans for together are close to each other and share the blocks they can skip (FPS order
-  // scatters consecutive centres all over the cloud).  Any assignment gives the same output.
-  if (warp == 0) {
-    const int lc0 = static_cast<int>(lane);
-    float key = (lc0 < live_centres) ? a.new_xyz[(static_cast<size_t>(b) * a.m + jc0 + lc0) * 3 + 1]
-                                     : __int_as_float(0x7f800000);
-    if (!(key == key)) key = __int_as_float(0x7f800000);  // NaN sorts last
-    int val = lc0;
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1) {  // bitonic sort of (key, val) across the warp
-#pragma unroll
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        const float ok = __shfl_xor_sync(0xffffffffu, key, j);
-        const int ov = __shfl_xor_sync(0xffffffffu, val, j);
-        const bool up = ((lane & k) == 0);
-        const bool lower = ((lane & j) == 0);
-        const bool less = (ok < key) || (ok == key && ov < val);
-        const bool take = (lower == up) ? less : !less && !(ok == key && ov == val);
-        if (take) { key = ok; val = ov; }
-      }
-    }
-    s_perm[lane] = val;
-  }
+  // the CTA's centres: TJ consecutive entries of the cloud's y-sorted centre list
+  if (threadIdx.x < TJ)
+    s_cent[threadIdx.x] = (static_cast<int>(threadIdx.x) < live_centres)
+                              ? __ldg(a.perm + static_cast<size_t>(b) * a.m + jc0 + threadIdx.x)
+                              : 0;
   __syncthreads();
   // ---------------- phase 1: warp w scans for the centres in scan slots w*CW .. w*CW+CW-1 ------------
   // No tile staging, no CTA barriers: every warp walks the cloud on its own (L1/L2-resident, 384
@@ -322,10 +357,10 @@ __global__ void __launch_bounds__(kQgThreads, 2) query_group_kernel(QgArgs a) {
   bool warp_open = false;
 #pragma unroll
   for (int q = 0; q < CW; ++q) {
-    const int lc = s_perm[static_cast<int>(warp) * CW + q];
+    const int lc = static_cast<int>(warp) * CW + q;
     lcs[q] = lc;
     const bool live = lc < live_centres;
-    const float *p = a.new_xyz + (static_cast<size_t>(b) * a.m + jc0 + (live ? lc : 0)) * 3;
+    const float *p = a.new_xyz + (static_cast<size_t>(b) * a.m + (live ? s_cent[lc] : 0)) * 3;
     cx[q] = p[0];
     cy[q] = p[1];
     cz[q] = p[2];
@@ -342,17 +377,28 @@ __global__ void __launch_bounds__(kQgThreads, 2) query_group_kernel(QgArgs a) {
       }
     }
   }
-  for (int sb = 0; sb < nsup && warp_open; ++sb) {
-    if (qg_box_dist2(ub, s_sup + sb * 6) > r2skip) continue;
-    const int g_end = min(sb * 8 + 8, nblk);
-    for (int g = sb * 8; g < g_end && warp_open; ++g) {
-      if (qg_box_dist2(ub, s_box + g * 6) > r2skip) continue;
+  for (int gb = 0; gb < nblk && warp_open; gb += 32) {
+    // 32 box tests at once (lane l: block gb + l), then only the blocks that can hold a neighbour
+    const int gl = gb + static_cast<int>(lane);
+    unsigned cand = __ballot_sync(0xffffffffu, gl < nblk && !(qg_box_dist2(ub, s_box + gl * 6) > r2skip));
+    while (cand && warp_open) {
+      const int g = gb + __ffs(cand) - 1;
+      cand &= cand - 1;
       const int k_end = min((g + 1) * blk, a.n);
-      for (int off = g * blk; off < k_end; off += 32) {
-        const int kk = off + static_cast<int>(lane);
-        const bool in = kk < k_end;
-        const float *pt = cloud + static_cast<size_t>(in ? kk : off) * 3;
-        const float x = __ldg(pt), y = __ldg(pt + 1), z = __ldg(pt + 2);
+      int off = g * blk;
+      bool in = off + static_cast<int>(lane) < k_end;
+      const float *pt = cloud + static_cast<size_t>(in ? off + static_cast<int>(lane) : off) * 3;
+      float x = __ldg(pt), y = __ldg(pt + 1), z = __ldg(pt + 2);
+      for (; off < k_end; off += 32) {
+        // the next 32 points are on their way while these are tested
+        const int noff = off + 32;
+        bool nin = false;
+        float nx = 0.f, ny = 0.f, nz = 0.f;
+        if (noff < k_end) {
+          nin = noff + static_cast<int>(lane) < k_end;
+          const float *np = cloud + static_cast<size_t>(nin ? noff + static_cast<int>(lane) : noff) * 3;
+          nx = __ldg(np); ny = __ldg(np + 1); nz = __ldg(np + 2);
+        }
 #pragma unroll
         for (int q = 0; q < CW; ++q) {
           const float d2 = ref_sqdist(cx[q] - x, cy[q] - y, cz[q] - z);
@@ -366,6 +412,7 @@ __global__ void __launch_bounds__(kQgThreads, 2) query_group_kernel(QgArgs a) {
               qg_append(hb, cntb[q], firstb[q], nsb, rows_b + lcs[q] * nsb, off, lane);
           }
         }
+        x = nx; y = ny; z = nz; in = nin;
       }
       bool open = false;
 #pragma unroll
@@ -373,57 +420,103 @@ __global__ void __launch_bounds__(kQgThreads, 2) query_group_kernel(QgArgs a) {
       warp_open = open;  // every ball of this warp is full: nothing further can be appended
     }
   }
-  // pad the rows: slots >= cnt repeat the first hit (0 for an empty ball: torch::zeros, ball_query.cpp:19)
+  // pad the rows (slots >= cnt repeat the first hit; 0 for an empty ball: torch::zeros,
+  // ball_query.cpp:19) and hand them out: idx[b][centre][0:ns]
   __syncwarp();
 #pragma unroll
   for (int q = 0; q < CW; ++q) {
     const int lc = lcs[q];
     if (lc < live_centres) {
-      for (int s = min(cnta[q], nsa) + static_cast<int>(lane); s < nsa; s += 32) rows_a[lc * nsa + s] = firsta[q];
+      const size_t cent = static_cast<size_t>(b) * a.m + s_cent[lc];
+      for (int s = static_cast<int>(lane); s < nsa; s += 32)
+        a.s[0].idx[cent * nsa + s] = s < cnta[q] ? rows_a[lc * nsa + s] : firsta[q];
       if (DUAL)
-        for (int s = min(cntb[q], nsb) + static_cast<int>(lane); s < nsb; s += 32) rows_b[lc * nsb + s] = firstb[q];
+        for (int s = static_cast<int>(lane); s < nsb; s += 32)
+          a.s[1].idx[cent * nsb + s] = s < cntb[q] ? rows_b[lc * nsb + s] : firstb[q];
     }
   }
-  __syncthreads();
+}
 
-  // ---------------- phase 2 ------------------------------------------------------------------------
-  qg_write_scale(a, a.s[0], b, jc0, live_centres, rows_a, s_tr);
-  if (DUAL) qg_write_scale(a, a.s[1], b, jc0, live_centres, rows_b, s_tr);
+// grid (ceil(M*ns / kQgGroupSlots), B, scales): the grouped tensor of one scale from its idx
+__global__ void __launch_bounds__(kQgThreads, 3) group_write_kernel(QgArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int *s_rows = reinterpret_cast<int *>(smem_raw);
+  float *s_tr = reinterpret_cast<float *>(smem_raw + QgGroupSmem::rows_bytes);
+  const QgScale &sc = a.s[blockIdx.z];
+  if (!sc.out) return;
+  const int b = blockIdx.y;
+  const long long total = static_cast<long long>(a.m) * sc.ns;
+  const long long slot0 = static_cast<long long>(blockIdx.x) * kQgGroupSlots;
+  if (slot0 >= total) return;
+  const int nslots = static_cast<int>(min(static_cast<long long>(kQgGroupSlots), total - slot0));
+  const int *src = sc.idx + static_cast<size_t>(b) * total + slot0;
+  for (int s = threadIdx.x; s < nslots; s += kQgThreads) s_rows[s] = __ldg(src + s);
+  __syncthreads();
+  qg_write_scale(a, sc, b, static_cast<int>(slot0), nslots, s_rows, s_tr);
 }
 
 template <int CW, bool DUAL>
 int qg_launch(const QgArgs &a, int b, cudaStream_t st) {
-  auto kern = query_group_kernel<CW, DUAL>;
+  const int nblk = ceil_div(a.n, a.blk);
+  const size_t smem = kQgMaxSlots * sizeof(int) + static_cast<size_t>(nblk) * 6 * sizeof(float);
+  dim3 grid(ceil_div(a.m, kQgWarps * CW), b);
+  ball_scan_kernel<CW, DUAL><<<grid, kQgThreads, smem, st>>>(a);
+  return check_launch("ball_scan_kernel");
+}
+
+int qg_launch_group(const QgArgs &a, int b, bool dual, cudaStream_t st) {
+  if (!a.s[0].out && !(dual && a.s[1].out)) return PVN3D_OK;
   static PerDeviceOnce once;
   if (once.first_time())
-    PVN3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)QgSmem::total),
-                   "query_group smem attr");
-  dim3 grid(ceil_div(a.m, kQgWarps * CW), b);
-  kern<<<grid, kQgThreads, QgSmem::total, st>>>(a);
-  return check_launch("query_group_kernel");
+    PVN3D_CUDA_TRY(cudaFuncSetAttribute(group_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)QgGroupSmem::total),
+                   "group_write smem attr");
+  const int ns_max = std::max(a.s[0].ns, dual ? a.s[1].ns : 0);
+  const long long groups = (static_cast<long long>(a.m) * ns_max + kQgGroupSlots - 1) / kQgGroupSlots;
+  if (groups > 0x7fffffffll) return PVN3D_ERR_UNSUPPORTED;
+  dim3 grid(static_cast<unsigned>(groups), b, dual ? 2 : 1);
+  group_write_kernel<<<grid, kQgThreads, QgGroupSmem::total, st>>>(a);
+  return check_launch("group_write_kernel");
 }
 
 int qg_dispatch_launch(QgArgs &a, int b, bool dual, cudaStream_t st);
 
 int qg_dispatch(QgArgs &a, int b, bool dual, cudaStream_t st) {
   a.blk = 128;
-  while (ceil_div(a.n, a.blk) > 896) a.blk *= 2;  // box table lives in 24 KB of shared memory
-  const int nblk = ceil_div(a.n, a.blk), nsup = ceil_div(nblk, 8);
+  while (ceil_div(a.n, a.blk) > kQgMaxBlocks) a.blk *= 2;  // box table lives in 24 KB of shared memory
+  const int nblk = ceil_div(a.n, a.blk);
   int rc0 = keep_async_pool_warm();
   if (rc0 != PVN3D_OK) return rc0;
-  float *boxes = nullptr;  // stream-ordered scratch: [B][nblk+nsup][6] floats (2.6 KB per 12288-pt cloud)
-  PVN3D_CUDA_TRY(cudaMallocAsync(&boxes, sizeof(float) * 6 * static_cast<size_t>(b) * (nblk + nsup), st),
-                 "query_group box scratch");
-  qg_boxes_kernel<<<dim3(ceil_div(nblk, 8), b), 256, 0, st>>>(a.xyz, a.n, a.blk, nblk, nsup, boxes);
+  // stream-ordered scratch: boxes [B][nblk][6] floats (2.3 KB per 12288-pt cloud), scan order [B][M],
+  // and idx [B][M][ns] of every scale whose idx the caller did not ask for
+  const size_t box_bytes = align_up(sizeof(float) * 6 * static_cast<size_t>(b) * nblk, 256);
+  const size_t perm_bytes = align_up(sizeof(int) * static_cast<size_t>(b) * a.m, 256);
+  size_t idx_bytes[2] = {0, 0};
+  for (int i = 0; i < (dual ? 2 : 1); ++i)
+    if (!a.s[i].idx) idx_bytes[i] = align_up(sizeof(int) * static_cast<size_t>(b) * a.m * a.s[i].ns, 256);
+  unsigned char *scratch = nullptr;
+  PVN3D_CUDA_TRY(cudaMallocAsync(&scratch, box_bytes + perm_bytes + idx_bytes[0] + idx_bytes[1], st),
+                 "query_group scratch");
+  float *boxes = reinterpret_cast<float *>(scratch);
+  int *perm = reinterpret_cast<int *>(scratch + box_bytes);
+  if (idx_bytes[0]) a.s[0].idx = reinterpret_cast<int *>(scratch + box_bytes + perm_bytes);
+  if (idx_bytes[1]) a.s[1].idx = reinterpret_cast<int *>(scratch + box_bytes + perm_bytes + idx_bytes[0]);
+  qg_boxes_kernel<<<dim3(ceil_div(nblk, 8), b), 256, 0, st>>>(a.xyz, a.n, a.blk, nblk, boxes);
   int rc = check_launch("qg_boxes_kernel");
   if (rc == PVN3D_OK) {
-    qg_supboxes_kernel<<<dim3(ceil_div(nsup * 6, 128), b), 128, 0, st>>>(nblk, nsup, boxes);
-    rc = check_launch("qg_supboxes_kernel");
+    if (a.m <= kQgSortMax) {
+      qg_sort_centres_kernel<<<b, 1024, 0, st>>>(a.new_xyz, a.m, perm);
+      rc = check_launch("qg_sort_centres_kernel");
+    } else {
+      qg_identity_perm_kernel<<<dim3(ceil_div(a.m, 256), b), 256, 0, st>>>(a.m, perm);
+      rc = check_launch("qg_identity_perm_kernel");
+    }
   }
   a.boxes = boxes;
+  a.perm = perm;
   if (rc == PVN3D_OK) rc = qg_dispatch_launch(a, b, dual, st);
-  cudaFreeAsync(boxes, st);
+  if (rc == PVN3D_OK) rc = qg_launch_group(a, b, dual, st);
+  cudaFreeAsync(scratch, st);
   return rc;
 }
 

@@ -16,9 +16,9 @@ echo "== ncu full: mlp_layer_kernel (32 launches per step: skip 3 warm-up steps)
 timeout 900 ncu --set full --clock-control none -k regex:mlp_layer_kernel -s 96 -c 32 \
     -f -o gpurun_out/prof_mlp_${TAG} python bench.py --steps 1 --warmup 3 --no-cpu-baseline \
     > gpurun_out/ncu_mlp_${TAG}.log 2>&1
-echo "== ncu full: query_group_kernel (roofline section of bench.py)"
-timeout 900 ncu --set full --clock-control none -k regex:query_group_kernel -s 0 -c 8 \
-    -f -o gpurun_out/prof_qg_${TAG} python bench.py --steps 1 --warmup 3 --no-cpu-baseline \
+echo "== ncu full: ball_scan_kernel + group_write_kernel (tools/qg_roofline.py)"
+timeout 900 ncu --set full --clock-control none -k "regex:ball_scan_kernel|group_write_kernel" -c 8 \
+    -f -o gpurun_out/prof_qg_${TAG} python tools/qg_roofline.py \
     > gpurun_out/ncu_qg_${TAG}.log 2>&1
 echo "== ncu full: ms_iterate_kernel"
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:ms_iterate_kernel -s 6 -c 2 \
