@@ -46,13 +46,19 @@ class FramePipeline:
         else:
             raise ValueError(shape)
         self.allow_tf32 = allow_tf32
-        # device staging buffers for run_host()
+        # device staging buffers for run_host(): two sets, so that the H2D copies of call i (on their own
+        # stream) run under the kernels of call i-1
         f32 = dict(dtype=torch.float32, device=self.dev)
-        self.d_cloud = torch.empty((self.b, self.n, 9), **f32)
-        self.d_pcld = torch.empty((self.b, self.n, 3), **f32)
-        self.d_labels = torch.empty((self.b, self.n), dtype=torch.int32, device=self.dev)
-        self.d_ctr_of = torch.empty((self.b, self.n, 3), **f32)
-        self.d_kp_of = torch.empty((self.b, self.k, self.n, 3), **f32)
+        self._sets = [dict(cld_rgb_nrm=torch.empty((self.b, self.n, 9), **f32),
+                           pcld=torch.empty((self.b, self.n, 3), **f32),
+                           labels=torch.empty((self.b, self.n), dtype=torch.int32, device=self.dev),
+                           ctr_of=torch.empty((self.b, self.n, 3), **f32),
+                           kp_of=torch.empty((self.b, self.k, self.n, 3), **f32)) for _ in range(2)]
+        self._set_free = [None, None]     # event: the kernels that last read the set are done
+        self._turn = 0
+        self._copy_stream = torch.cuda.Stream(self.dev)
+        self.d_cloud, self.d_pcld, self.d_labels, self.d_ctr_of, self.d_kp_of = (
+            self._sets[0][k] for k in ("cld_rgb_nrm", "pcld", "labels", "ctr_of", "kp_of"))
         self.h_poses = torch.empty((self.b, self.n_cls, 3, 4), dtype=torch.float32).pin_memory()
         self.h_present = torch.empty((self.b, self.n_cls), dtype=torch.uint8).pin_memory()
         self.features = None
@@ -86,15 +92,27 @@ class FramePipeline:
     @torch.no_grad()
     def run_host(self, hb: Dict[str, torch.Tensor]):
         """hb: pinned host tensors (pin_batch).  H2D copies, both hot paths, D2H of the poses; the
-        caller synchronises the stream before reading the returned pinned host tensors."""
+        caller synchronises the stream before reading the returned pinned host tensors.  The copies
+        go through a second stream into one of two staging sets: back-to-back calls overlap the
+        upload of call i with the kernels of call i-1."""
         b = hb["pcld"].shape[0]
-        self.d_cloud[:b].copy_(hb["cld_rgb_nrm"], non_blocking=True)
-        self.d_pcld[:b].copy_(hb["pcld"], non_blocking=True)
-        self.d_labels[:b].copy_(hb["labels"], non_blocking=True)
-        self.d_ctr_of[:b].copy_(hb["ctr_of"], non_blocking=True)
-        self.d_kp_of[:b].copy_(hb["kp_of"], non_blocking=True)
-        poses, present = self.run_device(self.d_cloud[:b], self.d_pcld[:b], self.d_labels[:b],
-                                         self.d_ctr_of[:b], self.d_kp_of[:b])
+        turn = self._turn
+        self._turn ^= 1
+        st = self._sets[turn]
+        cur = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self._copy_stream):
+            if self._set_free[turn] is not None:
+                self._copy_stream.wait_event(self._set_free[turn])
+            for key in ("cld_rgb_nrm", "pcld", "labels", "ctr_of", "kp_of"):
+                st[key][:b].copy_(hb[key], non_blocking=True)
+            uploaded = torch.cuda.Event()
+            uploaded.record(self._copy_stream)
+        cur.wait_event(uploaded)
+        poses, present = self.run_device(st["cld_rgb_nrm"][:b], st["pcld"][:b], st["labels"][:b],
+                                         st["ctr_of"][:b], st["kp_of"][:b])
+        done = torch.cuda.Event()
+        done.record(cur)
+        self._set_free[turn] = done
         self.h_poses[:b].copy_(poses, non_blocking=True)
         self.h_present[:b].copy_(present, non_blocking=True)
         return self.h_poses[:b], self.h_present[:b]
