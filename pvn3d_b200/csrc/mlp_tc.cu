@@ -242,28 +242,6 @@ __device__ __forceinline__ void rows_setup(const MlpArgs &a, long long p_first, 
   }
 }
 
-// element k of logical row p (slow path: chunks that straddle a segment boundary / unaligned rows)
-template <int PRO>
-__device__ __forceinline__ float row_elem(const MlpArgs &a, const RowState &s, int j, long long p, int k) {
-  if (PRO == PRO_DENSE) return k < a.a_cols ? __ldg(s.row[j] + k) : 0.f;
-  if (PRO == PRO_SA_GATHER) {
-    if (k < a.c_feat) return __ldg(s.row[j] + k);
-    const int d = k - a.c_feat;
-    if (d > 2) return 0.f;
-    // grouped_xyz -= new_xyz (pointnet2_utils.py:314)
-    return __ldg(a.xyz + static_cast<size_t>(s.qrow[j]) * 3 + d) -
-           __ldg(a.new_xyz + static_cast<size_t>(s.crow[j]) * 3 + d);
-  }
-  if (k < a.c2) {
-    const float *kf = a.known_feat + k;
-    return __fmaf_rn(__ldg(kf + static_cast<size_t>(s.g3[j]) * a.c2), s.w3[j],
-                     __fmaf_rn(__ldg(kf + static_cast<size_t>(s.g1[j]) * a.c2), s.w1[j],
-                               __fmul_rn(__ldg(kf + static_cast<size_t>(s.g2[j]) * a.c2), s.w2[j])));
-  }
-  const int d = k - a.c2;
-  return d < a.c1 ? __ldg(a.skip + p * a.lds + d) : 0.f;
-}
-
 __device__ __forceinline__ void sts_tf32(uint32_t addr, const float4 &v) {
   sts128(addr, to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
 }
@@ -335,19 +313,48 @@ __device__ __forceinline__ void stage_a_chunk(const MlpArgs &a, const RowState &
       return;
     }
   }
-  // generic path: element by element
+  // generic path (chunks that straddle a segment boundary / unaligned rows).  Which source an element
+  // comes from depends only on its column, not on the row, so the loads of the 8 passes are issued
+  // together as predicated loads -- no per-element branches, one round trip instead of 32.
+  float vv[8][4];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    float4 v = zero;
-    if ((s.live >> j) & 1u) {
-      const long long p = p_first + 4 * j;
-      v.x = row_elem<PRO>(a, s, j, p, k);
-      v.y = row_elem<PRO>(a, s, j, p, k + 1);
-      v.z = row_elem<PRO>(a, s, j, p, k + 2);
-      v.w = row_elem<PRO>(a, s, j, p, k + 3);
+    const bool live = (s.live >> j) & 1u;
+    const long long p = p_first + 4 * j;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int kk = k + e;
+      float v = 0.f;
+      if (PRO == PRO_DENSE) {
+        const bool on = live && kk < a.a_cols;
+        v = on ? __ldg(s.row[j] + (on ? kk : 0)) : 0.f;
+      } else if (PRO == PRO_SA_GATHER) {
+        const bool isf = live && kk < a.c_feat;
+        const int d = kk - a.c_feat;
+        const bool isx = live && d >= 0 && d <= 2;
+        const float f = isf ? __ldg(s.row[j] + (isf ? kk : 0)) : 0.f;
+        // grouped_xyz -= new_xyz (pointnet2_utils.py:314)
+        const float px = isx ? __ldg(a.xyz + static_cast<size_t>(s.qrow[j]) * 3 + (isx ? d : 0)) : 0.f;
+        const float pc = isx ? __ldg(a.new_xyz + static_cast<size_t>(s.crow[j]) * 3 + (isx ? d : 0)) : 0.f;
+        v = isf ? f : px - pc;
+      } else {
+        const bool isk = live && kk < a.c2;
+        const int d = kk - a.c2;
+        const bool iss = live && d >= 0 && d < a.c1;
+        const float *kf = a.known_feat + (isk ? kk : 0);
+        const float p1 = isk ? __ldg(kf + static_cast<size_t>(s.g1[j]) * a.c2) : 0.f;
+        const float p2 = isk ? __ldg(kf + static_cast<size_t>(s.g2[j]) * a.c2) : 0.f;
+        const float p3 = isk ? __ldg(kf + static_cast<size_t>(s.g3[j]) * a.c2) : 0.f;
+        const float sk = iss ? __ldg(a.skip + p * a.lds + (iss ? d : 0)) : 0.f;
+        // same contraction as three_interpolate (pn2_ops.cu): fma(p3,w3, fma(p1,w1, p2*w2))
+        v = isk ? __fmaf_rn(p3, s.w3[j], __fmaf_rn(p1, s.w1[j], __fmul_rn(p2, s.w2[j]))) : sk;
+      }
+      vv[j][e] = v;
     }
-    sts_tf32(sa + sw128_off(r_first + 4 * j, sub), v);
   }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    sts_tf32(sa + sw128_off(r_first + 4 * j, sub), make_float4(vv[j][0], vv[j][1], vv[j][2], vv[j][3]));
 }
 
 // ---- epilogue helpers ------------------------------------------------------------------------------
