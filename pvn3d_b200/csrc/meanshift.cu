@@ -665,6 +665,22 @@ __global__ void __launch_bounds__(kMsThreads, 3) ms_iterate_kernel(MsArgs a) {
     const int warps_total = kMsWarps * static_cast<int>(gridDim.x);
     int spw = 16;
     while (spw > 1 && total_seeds < spw * warps_total) spw >>= 1;
+    // ... or up to 4x fewer, if that fills the last round of tiles better: tiles cost the same, so a
+    // phase takes ceil(tiles / CTAs) rounds of (spw + staging) -- 624 tiles on 444 CTAs waste 30 %
+    if (split && spw >= 2) {
+      int best = spw;
+      long long best_cost = 0x7fffffffffffffffll;
+      for (int c = spw; c >= 1 && c * 4 >= spw; c >>= 1) {
+        int lt = 0;
+        for (int f = f_lo; f < f_hi; ++f) lt += (sm.prefix[f] + kMsWarps * c - 1) / (kMsWarps * c);
+        int tiles_c;
+        (void)block_exclusive_scan<kMsThreads>(lt, sm.warp_scan, &tiles_c);
+        const long long rounds = (tiles_c + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+        const long long cost = rounds * (c + 1);
+        if (cost < best_cost) { best_cost = cost; best = c; }
+      }
+      spw = best;
+    }
     // last phases: fewer seeds than warps on one CTA per SM -> smaller tiles (1, 2 or 4 live warps)
     int warps_live = kMsWarps;
     if (split && spw == 1)

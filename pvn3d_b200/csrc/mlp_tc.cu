@@ -107,9 +107,10 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, unsign
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
                : "memory");
 }
-// the mbarrier gets one (pre-counted) arrival when all cp.async issued so far by this thread landed
-__device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                           uint32_t idesc, uint32_t accumulate) {
@@ -401,7 +402,7 @@ __device__ __forceinline__ void warp_colmax_8(float (&v)[32], unsigned lane) {
 }
 
 struct MlpSmemCtl {
-  uint64_t full[kMlpMaxStages];   // 256 arrivals: every producer thread of the filling group, twice
+  uint64_t full[kMlpMaxStages];   // 128 arrivals: every producer thread of the filling group
   uint64_t empty[kMlpMaxStages];  // 1 arrival: tcgen05.commit of the MMAs that read the stage
   uint64_t acc_full[2];           // 1 arrival: tcgen05.commit after a tile's last MMA
   uint64_t acc_empty[2];          // 128 arrivals: the epilogue threads, once they have read it
@@ -434,7 +435,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_layer_kernel(const __grid_
   if (warp == kMlpEpiWarps + kMlpProWarps) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
-        mbar_init(&ctl.full[s], 256);
+        mbar_init(&ctl.full[s], 128);
         mbar_init(&ctl.empty[s], 1);
       }
       for (int b = 0; b < 2; ++b) {
@@ -468,6 +469,7 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_layer_kernel(const __grid_
     if (PRO == PRO_FP_INTERP)
       vec_ok = (a.c2 % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.known_feat) & 15u) == 0);
     const bool a_async = PRO == PRO_DENSE && a.a_tf32 && vec_ok;
+    int pend0 = 0, pend1 = 0, npend = 0;  // stages whose copies are committed but not yet published
     long long it_base = 0;  // number of K chunks staged before this tile (same in every role)
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it_base += kc_total) {
       if (kc_total == 1 && static_cast<unsigned>(it_base & 1) != grp) continue;  // other group's tile
@@ -483,6 +485,15 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_layer_kernel(const __grid_
         const long long it = it_base + kc;
         if (static_cast<unsigned>(it & 1) != grp) continue;
         const int s = static_cast<int>(it % S);
+        // asynchronous path: two chunks of copies stay in flight per thread; the older one is
+        // published (complete -> proxy fence -> arrive) before this thread can block on a free stage
+        if (npend == 2) {
+          cp_async_wait<1>();
+          fence_proxy_async_smem();  // landed cp.async data (generic proxy) -> tensor-core (async) proxy
+          mbar_arrive(&ctl.full[pend0]);
+          pend0 = pend1;
+          npend = 1;
+        }
         mbar_wait(&ctl.empty[s], static_cast<unsigned>(((it / S) & 1) ^ 1));
         const uint32_t sa = ring + static_cast<uint32_t>(s) * stage_bytes;
         const uint32_t sb = sa + a_bytes;
@@ -497,14 +508,29 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_layer_kernel(const __grid_
           for (int j = 0; j < 8; ++j)
             cp_async16(sa + sw128_off(r_first + 4 * j, sub), rs.row[j] + (k < a.a_cols ? k : 0),
                        (((rs.live >> j) & 1u) && k < a.a_cols) ? 16u : 0u);
-          cp_async_arrive_noinc(&ctl.full[s]);
+          cp_async_commit();
+          if (npend == 0) pend0 = s; else pend1 = s;
+          ++npend;
         } else {
-          cp_async_arrive_noinc(&ctl.full[s]);
+          cp_async_commit();
           stage_a_chunk<PRO>(a, rs, p_first, r_first, sub, kc * 32, sa, vec_ok);
-          fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor-core (async) proxy
+          cp_async_wait<0>();        // the weights of this chunk (issued before the A gather) have landed
+          fence_proxy_async_smem();  // generic-proxy stores / copies -> visible to the tensor-core proxy
+          mbar_arrive(&ctl.full[s]);
         }
-        mbar_arrive(&ctl.full[s]);
       }
+    }
+    if (npend == 2) {
+      cp_async_wait<1>();
+      fence_proxy_async_smem();
+      mbar_arrive(&ctl.full[pend0]);
+      pend0 = pend1;
+      npend = 1;
+    }
+    if (npend == 1) {
+      cp_async_wait<0>();
+      fence_proxy_async_smem();
+      mbar_arrive(&ctl.full[pend0]);
     }
   } else if (warp < kMlpEpiWarps) {
     // ================= epilogue: warp w owns TMEM lanes 32w..32w+31 = rows p0+32w.. ==================

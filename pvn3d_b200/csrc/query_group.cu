@@ -19,13 +19,13 @@
 //              ~90 % of the scan on raster-ordered ones (the reference's samplers keep raster order).
 //              The next step's points are loaded while the current ones are tested.  Result: idx[B,M,S]
 //              (the caller's buffer, or stream-ordered scratch when only the grouped tensor is wanted).
-//   group      (group_write_kernel, 1024 consecutive output slots of one scale per CTA, 3 CTAs/SM)
+//   group      (group_write_kernel, 768 consecutive output slots of one scale per CTA, 3 CTAs/SM)
 //              descriptors are read POINT-MAJOR (feat_pm[B,N,ldf]).  A warp owns 32 consecutive slots:
 //              cp.async pulls 32 channels of four neighbours per instruction (8 lanes = one fully used
 //              128-byte run) into one of two private shared-memory tiles while the previous tile is
 //              written out as 16-byte stores -- 8 lanes cover one 128-byte line of a channel row, a
 //              warp instruction four rows -- after a 4x4 register transpose.  Every output byte is
-//              written once, in runs of 4 KB per channel and CTA; every gathered sector is fully used.
+//              written once, in runs of 3 KB per channel and CTA; every gathered sector is fully used.
 // Algorithmic HBM bytes per launch and scale:
 //   B * [ 12 N + 12 M + 4 C N  (reads)  +  4 M S + 4 (3+C) M S  (writes) ].
 #include "common.cuh"
@@ -37,7 +37,8 @@ constexpr int kQgThreads = 256;
 constexpr int kQgWarps = 8;
 constexpr int kQgMaxBlocks = 1024;  // bounding-box blocks per cloud (24 KB of shared memory at most)
 constexpr int kQgMaxSlots = 2048;   // scan: slots (centres x nsample, both scales) per CTA
-constexpr int kQgGroupSlots = 1024; // group: consecutive output slots of one scale per CTA
+constexpr int kQgGroupSlots = 768;  // group: consecutive output slots of one scale per CTA (75 KB of
+                                    // shared memory with the transpose tiles: three CTAs per SM)
 constexpr int kQgTrStride = 36;     // floats per row of a per-warp [32 slots][32 channels] tile
 constexpr int kQgTrFloats = 32 * kQgTrStride;  // one tile; every warp owns two (double buffering)
 static_assert(2 * kQgTrFloats >= 32 * 33, "scalar fallback transposes through the same buffer");
@@ -58,7 +59,7 @@ struct QgArgs {
 };
 
 struct QgGroupSmem {
-  static constexpr size_t rows_bytes = kQgGroupSlots * sizeof(int);                        // 4096
+  static constexpr size_t rows_bytes = kQgGroupSlots * sizeof(int);                        // 3072
   static constexpr size_t tr_bytes = kQgWarps * 2 * kQgTrFloats * sizeof(float);           // 73728
   static constexpr size_t total = rows_bytes + tr_bytes;
 };
