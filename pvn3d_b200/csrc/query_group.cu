@@ -54,6 +54,7 @@ struct QgArgs {
   int ldf, n, m, c;
   int blk;  // points per bounding-box block (multiple of 32; at most 896 blocks + their super boxes)
   const float *boxes;  // [B][nblk][6] from qg_boxes_kernel
+  int group_slots;     // output slots per CTA of group_write_kernel (<= kQgGroupSlots, multiple of 32)
   const int *perm;     // [B][M] centres in scan order (sorted by y) from qg_sort_centres_kernel
   QgScale s[2];
 };
@@ -447,9 +448,9 @@ __global__ void __launch_bounds__(kQgThreads, 3) group_write_kernel(QgArgs a) {
   if (!sc.out) return;
   const int b = blockIdx.y;
   const long long total = static_cast<long long>(a.m) * sc.ns;
-  const long long slot0 = static_cast<long long>(blockIdx.x) * kQgGroupSlots;
+  const long long slot0 = static_cast<long long>(blockIdx.x) * a.group_slots;
   if (slot0 >= total) return;
-  const int nslots = static_cast<int>(min(static_cast<long long>(kQgGroupSlots), total - slot0));
+  const int nslots = static_cast<int>(min(static_cast<long long>(a.group_slots), total - slot0));
   const int *src = sc.idx + static_cast<size_t>(b) * total + slot0;
   for (int s = threadIdx.x; s < nslots; s += kQgThreads) s_rows[s] = __ldg(src + s);
   __syncthreads();
@@ -465,7 +466,7 @@ int qg_launch(const QgArgs &a, int b, cudaStream_t st) {
   return check_launch("ball_scan_kernel");
 }
 
-int qg_launch_group(const QgArgs &a, int b, bool dual, cudaStream_t st) {
+int qg_launch_group(QgArgs &a, int b, bool dual, cudaStream_t st) {
   if (!a.s[0].out && !(dual && a.s[1].out)) return PVN3D_OK;
   static PerDeviceOnce once;
   if (once.first_time())
@@ -473,7 +474,12 @@ int qg_launch_group(const QgArgs &a, int b, bool dual, cudaStream_t st) {
                                         (int)QgGroupSmem::total),
                    "group_write smem attr");
   const int ns_max = std::max(a.s[0].ns, dual ? a.s[1].ns : 0);
-  const long long groups = (static_cast<long long>(a.m) * ns_max + kQgGroupSlots - 1) / kQgGroupSlots;
+  // slots per CTA: the full 768 when that still gives every SM its three CTAs twice over, else less
+  const long long all_slots = static_cast<long long>(b) * a.m * (a.s[0].ns + (dual ? a.s[1].ns : 0));
+  const long long want_ctas = 6ll * std::max(1, sm_count());
+  a.group_slots = kQgGroupSlots;
+  while (a.group_slots > 256 && all_slots / a.group_slots < want_ctas) a.group_slots -= 128;
+  const long long groups = (static_cast<long long>(a.m) * ns_max + a.group_slots - 1) / a.group_slots;
   if (groups > 0x7fffffffll) return PVN3D_ERR_UNSUPPORTED;
   dim3 grid(static_cast<unsigned>(groups), b, dual ? 2 : 1);
   group_write_kernel<<<grid, kQgThreads, QgGroupSmem::total, st>>>(a);
