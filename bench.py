@@ -144,6 +144,11 @@ def main():
     ap.add_argument("--engine", default="fused", choices=["fused", "modules"],
                     help="hot path A: fused tcgen05 engine (default) or module graph with cuDNN/cuBLAS MLPs")
     args = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON): everything any library prints to fd 1 from here on
+    # (NCCL prints its version there) goes to stderr; the JSON is written to the saved descriptor
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     args.warmup = max(args.warmup, 3 if args.impl == "b200" else 0)
     cfg = CONFIGS[args.config]
 
@@ -177,15 +182,14 @@ def main():
                 "cpu_baseline": {"value": value, "unit": "frames/s", "cores": n_threads, "kind": "port", "sample": desc},
                 "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
         return 0
 
     # ------------------------------------------------------------------ our arm
     from pvn3d_b200 import _ext, _lib
     from pvn3d_b200.pipeline import FramePipeline
 
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"     # keep stdout to the single JSON line
     rank, local_rank, world = pdist.init_from_env()
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     dev = torch.device(f"cuda:{local_rank}")
@@ -306,7 +310,8 @@ def main():
             line["meanshift_sweeps_frame0"] = iters
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     if world > 1:
         torch.distributed.destroy_process_group()
     return 0
