@@ -474,10 +474,6 @@ __device__ __forceinline__ void ms_run_tile_split(const MsArgs &a, MsIterSmem &s
     ms_stage_pairs(sm.pts, a.cpts + start, n_c);
     __syncthreads();
   }
-  const bool dbg = (a.flags & 4u) && it_lo == 209 && t == 0;
-  unsigned long long dbg_t0 = 0;
-  int dbg_c[3] = {0, 0, 0};
-  if (dbg) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
   int idx[SPL];
   float cx[SPL], cy[SPL], cz[SPL], last[SPL];
   bool frozen[SPL];
@@ -498,8 +494,6 @@ __device__ __forceinline__ void ms_run_tile_split(const MsArgs &a, MsIterSmem &s
     if (single && !warp_live) break;
     MsSeedQ sq[SPL];
     MsSeedS ss[SPL];
-    long long ck0 = 0, ck1 = 0, ck2 = 0;
-    if (dbg) ck0 = clock64();
 #pragma unroll
     for (int r = 0; r < SPL; ++r) {
       sq[r] = ms_seed_q(k, cx[r], cy[r], cz[r]);
@@ -522,7 +516,6 @@ __device__ __forceinline__ void ms_run_tile_split(const MsArgs &a, MsIterSmem &s
         }
       }
     }
-    if (dbg) ck1 = clock64();
     float sw[SPL], sx[SPL], sy[SPL], sz[SPL];
 #pragma unroll
     for (int r = 0; r < SPL; ++r) {
@@ -541,7 +534,6 @@ __device__ __forceinline__ void ms_run_tile_split(const MsArgs &a, MsIterSmem &s
         sz[r] += __shfl_xor_sync(0xffffffffu, sz[r], o);
       }
     }
-    if (dbg) ck2 = clock64();
     bool violates = false;
 #pragma unroll
     for (int r = 0; r < SPL; ++r) {
@@ -561,28 +553,11 @@ __device__ __forceinline__ void ms_run_tile_split(const MsArgs &a, MsIterSmem &s
     }
     if (__any_sync(0xffffffffu, violates) && lane == 0)
       atomicOr(a.viol + static_cast<size_t>(f) * a.viol_words + (it >> 5), 1u << (it & 31));
-    if (dbg && it == it_lo) {
-      dbg_c[0] = static_cast<int>(ck1 - ck0);
-      dbg_c[1] = static_cast<int>(ck2 - ck1);
-      dbg_c[2] = static_cast<int>(clock64() - ck2);
-    }
     if (!single) {
       bool fr = true;
 #pragma unroll
       for (int r = 0; r < SPL; ++r) fr &= frozen[r];
       if (!__syncthreads_or(fr ? 0 : 1)) break;
-    }
-  }
-  if (dbg) {
-    unsigned long long ns;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
-    const int slot = atomicAdd(a.cfg + 4, 1);
-    if (slot < 220) {
-      unsigned smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      int *rec = a.cfg + 256 + 8 * slot;
-      rec[0] = f; rec[1] = tile; rec[2] = n_c; rec[3] = n_act; rec[4] = static_cast<int>(smid);
-      rec[5] = static_cast<int>(ns - dbg_t0); rec[6] = dbg_c[0]; rec[7] = dbg_c[1];
     }
   }
   if (sub == 0) {

@@ -35,7 +35,3 @@ for p in range(60):
     if top[p] == 0: break
     nxt = top[p + 1] if p + 1 < 60 and top[p + 1] else done[p]
     print(f"phase {p:2d} seeds {seeds[p]:7d} tiles {tiles[p]:5d}  tiles {done[p]-top[p]:6d} us   sync+top {nxt-done[p]:5d} us")
-n = min(int(cfg[4]), 220)
-rec = cfg[256:256 + 8 * n].reshape(n, 8)
-print("probe tiles of the phase starting at it 209:", n, " columns: f tile n_c n_act smid total_ns sweep_cyc reduce_cyc")
-print(rec[np.argsort(rec[:, 5])][-40:])
