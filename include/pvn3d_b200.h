@@ -110,7 +110,9 @@ int pvn3d_transpose_cn_to_nc(const float *src_bcn, int b, int c, int n, float *d
 int pvn3d_transpose_nc_to_cn(const float *src_bnc, int b, int n, int c, float *dst_bcn,
                              pvn3d_stream_t stream);
 
-/* query_and_group: ball_query + group(xyz) - centre + group(features) + concat in ONE kernel.
+/* query_and_group: ball_query + group(xyz) - centre + group(features) + concat in ONE call (a scan
+ * kernel that finds idx and a gather/transpose kernel that writes the grouped tensor; neither the
+ * transposed cloud, nor the two grouped tensors, nor the concat copy of the reference exist).
  *   xyz[B,N,3], new_xyz[B,M,3], feat_pm[B,N,ldf] point-major rows whose first C columns are the
  *   descriptors (ldf >= C; C may be 0 -> feat_pm NULL)
  *   -> idx[B,M,S] (may be NULL), out[B,3+C,M,S]   == QueryAndGroup(radius,S,use_xyz=True).forward
@@ -120,7 +122,7 @@ int pvn3d_query_and_group(const float *xyz, const float *new_xyz, const float *f
                           int b, int n, int m, int c, float radius, int nsample, int *idx,
                           float *out, pvn3d_stream_t stream);
 
-/* The two scales of one multi-scale-grouping level in ONE launch (same centres, same cloud: every
+/* The two scales of one multi-scale-grouping level in ONE call (same centres, same cloud: every
  * squared distance is evaluated once and compared with both radii).  Per scale either output may be
  * NULL: out NULL = ball query only (idx), idx NULL = grouped tensor only. */
 int pvn3d_query_and_group2(const float *xyz, const float *new_xyz, const float *feat_pm, int ldf,
