@@ -131,3 +131,40 @@ def test_unmodified_reference_binds_to_the_drop_in():
         "print('ok')\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd="/tmp")
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_mlp_packing_folds_batchnorm_and_rounds_to_tf32():
+    """Host half of the tensor-core MLP path (pvn3d_b200/mlp.py): Conv2d(1x1)+BatchNorm2d(eval) folded into one
+    matrix + bias reproduces the module (pytorch_utils.py:25-50), weights are TF32 values (10-bit mantissa, ties
+    away = cvt.rna) zero-padded to the kernel's k_pad % 32 / n_pad % 16 grid, and the first SA layer's xyz
+    columns are moved behind the descriptor columns (the order pvn3d_mlp_sa_first's producer emits)."""
+    from pvn3d_b200 import mlp
+    x = torch.tensor([1.0, 1.0 + 2 ** -11, 1.0 + 2 ** -10, -3.0000002, 65504.5, 0.0, 1e-30])
+    r = mlp.tf32_round(x)
+    assert torch.equal(r.view(torch.int32) & 0x1FFF, torch.zeros_like(r, dtype=torch.int32))      # low 13 bits clear
+    assert r[1] == 1.0 + 2 ** -10 and r[0] == 1.0 and r[2] == x[2]                                  # tie rounds away
+    assert ((r - x).abs() <= x.abs() * 2 ** -11).all()
+
+    model = testing.seeded_pointnet2msg(0, 1).eval()
+    layer = model.SA_modules[1].mlps[0][0]                     # Conv2d(99 -> 64, no bias) + BN + ReLU
+    w, b = mlp.fold_conv_bn(layer)
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(2, w.shape[1], 7, 3, generator=g)
+    with torch.no_grad():
+        want = layer(a)                                        # ReLU(BN(conv(a)))
+    got = torch.relu(torch.einsum("nk,bkms->bnms", w, a) + b[None, :, None, None])
+    assert (got - want).abs().max() <= 1e-5 * max(1.0, want.abs().max())
+
+    pk = mlp.PackedLayer(w, b)
+    assert pk.k_pad % 32 == 0 and pk.n_pad % 16 == 0 and pk.k_pad >= w.shape[1] and pk.n_pad >= w.shape[0]
+    assert torch.equal(pk.w[: w.shape[0], : w.shape[1]], mlp.tf32_round(w))
+    assert pk.w[w.shape[0]:].abs().sum() == 0 and pk.w[:, w.shape[1]:].abs().sum() == 0 and pk.bias[w.shape[0]:].abs().sum() == 0
+    nxt = mlp.PackedLayer(torch.randn(40, w.shape[0], generator=g), torch.zeros(40), pk.n_pad)
+    assert nxt.k_pad >= pk.n_pad                               # consumes the padded activations of `pk`
+
+    eng_cols = torch.cat([w[:, 3:], w[:, :3]], dim=1)          # [xyz | feat] -> [feat | xyz]
+    assert torch.equal(eng_cols[:, -3:], w[:, :3]) and torch.equal(eng_cols[:, :-3], w[:, 3:])
+    assert mlp.MLP_RELU == 1 and mlp.MLP_ROUND_OUT == 2 and mlp.MLP_A_TF32 == 4          # include/pvn3d_b200.h
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "pvn3d_b200.h")).read()
+    for name, val in (("PVN3D_MLP_RELU", 1), ("PVN3D_MLP_ROUND_OUT", 2), ("PVN3D_MLP_A_TF32", 4)):
+        assert f"#define {name} {val}" in hdr
