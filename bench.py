@@ -396,9 +396,9 @@ def roofline_query_group(torch, _ext, dev, B, cloud, peak, peak_kind):
     big = max(per, key=lambda p: p["MB"])
     return {"kernel": "pvn3d_query_and_group2 = ball_scan_kernel + group_write_kernel (fused ball-query+group, both radii of a level per call: 4 calls of one batch)", "bound": "hbm",
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
-            # dram__bytes_read.sum + dram__bytes_write.sum of the same four calls from one `ncu --set full` capture
-            # (profiles/ncu_qgfull_r01o.md): BELOW the algorithmic bytes -- the descriptor tables are L2 hits
-            "traffic": 1856.1 if B == 32 else None, "traffic_unit": "MB per batch (ncu, profiles/ncu_qgfull_r01o.md)",
+            # dram__bytes_read.sum + dram__bytes_write.sum of the same four calls (8 kernels) from one `ncu --set full`
+            # capture (profiles/ncu_qgsplit_r01u.md): BELOW the algorithmic bytes -- the descriptor tables are L2 hits
+            "traffic": 2005.4 if B == 32 else None, "traffic_unit": "MB per batch (ncu, profiles/ncu_qgsplit_r01u.md)",
             "algorithmic_MB_per_batch": total_bytes / 1e6, "us_per_batch": total_ms * 1e3,
             "largest_launch": big, "per_launch": per}
 
