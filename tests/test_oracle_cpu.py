@@ -189,3 +189,25 @@ def test_pn2_oracle_matches_reference_gpu_recording(golden_dir):
             w /= w.sum(-1, keepdims=True)
             assert np.array_equal(pn2.three_interpolate(pf, nn, w), z["interp"])
         lvl = nxt
+
+
+def test_cell_list_ball_query_prototype_matches_oracle():
+    """tools/experiments/ball_cells.py (the round-2 design for the scan: voxel buckets + index-ordered hits)
+    returns the reference's ball_query bit for bit -- sparse, dense (more hits than nsample), empty balls,
+    duplicates, centres outside the cloud's bounding box."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "ball_cells", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "experiments", "ball_cells.py"))
+    bc = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bc)
+    rng = np.random.default_rng(11)
+    for n, m, radii, nss in [(3000, 64, (0.05, 0.1), (16, 32)), (800, 40, (0.3, 0.45), (8, 16)), (500, 30, (0.01, 0.02), (4, 8))]:
+        xyz = rng.uniform(-0.5, 0.5, size=(n, 3)).astype(np.float32)
+        xyz[n // 2: n // 2 + 20] = xyz[:20]                                   # exact duplicates
+        new = xyz[rng.choice(n, m, replace=False)].copy()
+        new[0] = [2.0, 2.0, 2.0]                                              # empty ball, outside the box
+        new[1] = xyz[5] + np.float32(radii[0]) * np.array([1, 0, 0], np.float32)   # a point right at the radius
+        got = bc.ball_query_cells(new, xyz, radii, nss, n_buckets=256)
+        for g, r, ns in zip(got, radii, nss):
+            want = pn2.ball_query(new[None], xyz[None], float(np.float32(r)), ns)[0]
+            assert np.array_equal(g, want), (n, r, ns)
