@@ -4,7 +4,7 @@ reference's exact semantics.
 The reference (`ball_query_gpu.cu:9-54`) scans the cloud in index order and keeps the first `nsample`
 points with d2 < r^2, padding with the first hit.  Equivalent without the O(N) scan per centre:
 
-  1. bin the cloud into voxels of edge >= r_max (x 1.00001: a neighbour is then always within +-1 voxel of
+  1. bin the cloud into voxels of edge >= r_max (x 1.001 -- far above the fp32 error of the binning even for grids of 1000 voxels: a neighbour is then always within +-1 voxel of
      the centre's voxel, whatever the rounding of the binning), hash the voxel to one of H buckets,
      counting-sort the point indices by bucket (stable: indices ascend inside a bucket);
   2. per centre: the <= 27 DISTINCT buckets of the neighbouring voxels give the candidates (hash
@@ -44,7 +44,7 @@ def ref_d2(c, p):
 
 
 def build_cells(xyz, r_max, n_buckets=4096):
-    cell = np.float64(r_max) * 1.00001
+    cell = np.float64(r_max) * 1.001
     lo = xyz.min(0).astype(np.float64)
     ijk = np.floor((xyz.astype(np.float64) - lo) / cell).astype(np.int64)
     h = _hash(ijk, n_buckets)
