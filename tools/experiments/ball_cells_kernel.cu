@@ -1,4 +1,11 @@
-// PROTOTYPE for round 2 (compiles, NOT linked into libpvn3d_b200.so, NOT yet run on a GPU):
+// PROTOTYPE for round 2 (NOT linked into libpvn3d_b200.so).  Run once on a B200 through
+// tools/experiments/ball_cells_test.cu at level-1 geometry (B=32, N=12288, M=2048, radii 0.0175/0.025):
+//   bit-exact (0 mismatches of 196 608 indices vs the CPU restatement, no centre over the list capacity), but
+//   cells_build 22 us + ball_cells 166 us  vs  ~150 us for the shipped ball_scan_kernel -- NOT yet a win:
+//   on a surface scene ~8 points fall into a voxel and most of the 27 neighbour buckets are empty, so the
+//   warp spends 27 dependent bucket look-ups on steps that fill 0-8 of its 32 lanes.  Next: prefix-sum the
+//   27 ranges and let the lanes walk the CONCATENATED candidate list (~200 candidates = 7 full steps).
+//
 // ball query by cell list with the reference's exact first-nsample-in-index-order semantics.
 // Algorithm + exactness argument: tools/experiments/ball_cells.py (checked against the oracle on CPU by
 // tests/test_oracle_cpu.py::test_cell_list_ball_query_prototype_matches_oracle).
