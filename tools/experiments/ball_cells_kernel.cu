@@ -3,8 +3,10 @@
 //   bit-exact (0 mismatches of 196 608 indices vs the CPU restatement, no centre over the list capacity), but
 //   cells_build 22 us + ball_cells 166 us  vs  ~150 us for the shipped ball_scan_kernel -- NOT yet a win:
 //   on a surface scene ~8 points fall into a voxel and most of the 27 neighbour buckets are empty, so the
-//   warp spends 27 dependent bucket look-ups on steps that fill 0-8 of its 32 lanes.  Next: prefix-sum the
-//   27 ranges and let the lanes walk the CONCATENATED candidate list (~200 candidates = 7 full steps).
+//   warp spends 27 dependent bucket look-ups on steps that fill 0-8 of its 32 lanes.  The kernel below is
+//   already v2 (prefix-summed ranges, lanes walk the CONCATENATED candidate list: ~200 candidates = 7 full
+//   steps) -- it compiles and passes the same harness build, but the GPU budget ran out before it could run:
+//   FIRST thing to do in round 2: `tools/experiments/ball_cells_test` (prints mismatches and both timings).
 //
 // ball query by cell list with the reference's exact first-nsample-in-index-order semantics.
 // Algorithm + exactness argument: tools/experiments/ball_cells.py (checked against the oracle on CPU by
@@ -140,6 +142,7 @@ __device__ __forceinline__ void warp_bitonic(int *v, int p2, unsigned lane) {
 
 __global__ void __launch_bounds__(kCellWarps * 32) ball_cells_kernel(CellArgs a) {
   __shared__ int s_list[kCellWarps][2][kCellListCap];
+  __shared__ int s_pre[kCellWarps][32], s_beg[kCellWarps][32];
   const int b = blockIdx.y;
   const unsigned lane = lane_id(), warp = threadIdx.x >> 5;
   const int j = blockIdx.x * kCellWarps + static_cast<int>(warp);
@@ -155,27 +158,42 @@ __global__ void __launch_bounds__(kCellWarps * 32) ball_cells_kernel(CellArgs a)
                                     ck + static_cast<int>(lane / 9) - 1);
   const unsigned same = __match_any_sync(0xffffffffu, bucket);
   const bool leader = lane < 27 && (__ffs(same) - 1) == static_cast<int>(lane);
-  unsigned todo = __ballot_sync(0xffffffffu, leader);
   const int *start = a.start + static_cast<size_t>(b) * (kCellBuckets + 1);
   const float4 *sorted = a.sorted + static_cast<size_t>(b) * a.n;
-  int cnt[2] = {0, 0};
-  while (todo) {
-    const int src = __ffs(todo) - 1;
-    todo &= todo - 1;
-    const unsigned bk = __shfl_sync(0xffffffffu, bucket, src);
-    const int s = start[bk], e = start[bk + 1];
-    for (int off = s; off < e; off += 32) {
-      const int q = off + static_cast<int>(lane);
-      const bool in = q < e;
-      const float4 p = sorted[in ? q : s];
-      const float d2 = ref_sqdist(cx - p.x, cy - p.y, cz - p.z);  // ball_query_gpu.cu:31-33
+  // v2 (not yet run): the <= 27 bucket ranges are CONCATENATED -- lane l owns range l, an exclusive
+  // prefix sum of the lengths gives every candidate a rank, and the warp walks the ranks 32 at a time
+  // (v1 walked bucket by bucket: 27 dependent look-ups for steps that filled 0-8 lanes on surface scenes)
+  const int rs = leader ? start[bucket] : 0;
+  const int rl = leader ? start[bucket + 1] - rs : 0;
+  int incl = rl;
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const unsigned hits = __ballot_sync(0xffffffffu, in && d2 < a.r2[r]);
-        const int slot = cnt[r] + __popc(hits & lanemask_lt());
-        if (((hits >> lane) & 1u) && slot < kCellListCap) s_list[warp][r][slot] = __float_as_int(p.w);
-        cnt[r] += __popc(hits);
-      }
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (static_cast<int>(lane) >= o) incl += v;
+  }
+  const int total = __shfl_sync(0xffffffffu, incl, 31);
+  s_pre[warp][lane] = incl - rl;  // rank of the first candidate of range `lane`
+  s_beg[warp][lane] = rs;
+  __syncwarp();
+  int cnt[2] = {0, 0};
+  for (int base = 0; base < total; base += 32) {
+    const int g = base + static_cast<int>(lane);
+    const bool in = g < total;
+    // owner = last range whose first rank is <= g (empty ranges share a rank with their successor and lose)
+    int lo_r = 0, hi_r = 31;
+    while (lo_r < hi_r) {
+      const int mid = (lo_r + hi_r + 1) >> 1;
+      if (s_pre[warp][mid] <= (in ? g : 0)) lo_r = mid; else hi_r = mid - 1;
+    }
+    const int q = s_beg[warp][lo_r] + ((in ? g : 0) - s_pre[warp][lo_r]);
+    const float4 p = sorted[in ? q : 0];
+    const float d2 = ref_sqdist(cx - p.x, cy - p.y, cz - p.z);  // ball_query_gpu.cu:31-33
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const unsigned hits = __ballot_sync(0xffffffffu, in && d2 < a.r2[r]);
+      const int slot = cnt[r] + __popc(hits & lanemask_lt());
+      if (((hits >> lane) & 1u) && slot < kCellListCap) s_list[warp][r][slot] = __float_as_int(p.w);
+      cnt[r] += __popc(hits);
     }
   }
   __syncwarp();
