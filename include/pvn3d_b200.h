@@ -187,6 +187,16 @@ int pvn3d_three_nn_weights(const float *dist2, long long rows, float *weight, pv
 #define PVN3D_MS_STRICT 0u      /* the reference's global stop rule decides the iteration count T */
 #define PVN3D_MS_EARLY_EXIT 1u  /* additionally stop a fit once the RETURNED seed is stationary    */
 #define PVN3D_MS_NO_FREEZE 2u   /* validation: keep sweeping seeds that have stopped moving        */
+#define PVN3D_MS_DEBUG_TIMING 4u /* phase time stamps in the head of the workspace                 */
+/* PVN3D_MS_CERTIFIED (the default of the Python surface): the returned seed is iterated on its own
+ * until it is stationary (iteration s); it0 <= s is the first iteration from which its remaining
+ * path to C_s is shorter than 1e-5*bandwidth.  A fit is CERTIFIED when, for every iteration
+ * it < it0, some witness seed (far-from-mode / low-density inputs, iterated alongside) still moves by
+ * >= bandwidth*1e-3 -- then the reference's global stop rule cannot fire before it0 (T >= it0), and
+ * the returned C_s is within 1e-5*bandwidth (+ the drift of a stationary seed) of the reference's
+ * C_T.  ctr.w reports it0 (a lower bound of the reference's T).  Fits that cannot be certified fall
+ * back to PVN3D_MS_EARLY_EXIT over all seeds, which applies the reference's rule exactly. */
+#define PVN3D_MS_CERTIFIED 8u
 
 /* A batch of F independent MeanShiftTorch(bandwidth, max_iter).fit(A_f) problems.
  *   pts        [cap,4] f32  vote clouds (x,y,z,unused); fit f owns rows
@@ -233,6 +243,12 @@ int pvn3d_best_fit_transform_batch(const float *a, const float *b, const uint8_t
  *   new_mask [B,N] i32           relabelled mask of the filter pass (NULL to skip)        (:66-72)
  * use_ctr must be 1 (the reference's use_ctr=False branch is never exercised: SURVEY App. A.5). */
 size_t pvn3d_frame_poses_workspace_bytes(int b, int n, int k, int n_cls, int max_iter);
+/* byte offset, inside that workspace, of the mean-shift workspace of the LAST launch (all centre +
+ * keypoint fits); int32 word PVN3D_MS_STAT_CERTIFIED of it counts the fits PVN3D_MS_CERTIFIED closed
+ * without sweeping all seeds (diagnostics for bench.py; same word at the head of a
+ * pvn3d_meanshift_fit_batch workspace). */
+#define PVN3D_MS_STAT_CERTIFIED 8
+size_t pvn3d_frame_poses_ms_workspace_offset(int b, int n, int k, int n_cls, int max_iter);
 int pvn3d_frame_poses_batch(const float *pcld, const int *mask, const float *ctr_of,
                             const float *kp_of, int b, int n, int k, int n_cls,
                             const float *mesh_kps, const float *cls_radius, int use_ctr_clus_flter,

@@ -20,6 +20,17 @@ if [ ! -d "$REF" ]; then
   exit 0
 fi
 mkdir -p "$OUT/obj"
+# Stage the reference PYTHON the GPU-side tests and bench.py's stock-GPU baseline import (the GPU box
+# has no /root/reference): lib/ (without the 84 MB ResNet checkpoint), common.py and the keypoint /
+# radius text fixtures under datasets/.  Verbatim copies into the git-ignored oracle/_ref/py -- test
+# infrastructure that travels with the gpurun snapshot; never part of the repository history.
+PYREF="$(dirname "$REF")"
+if [ -d "$PYREF/lib" ]; then
+  rm -rf "$OUT/py"; mkdir -p "$OUT/py"
+  tar -C "$PYREF" --exclude='ResNet_pretrained_mdl' --exclude='__pycache__' --exclude='*.pyc' -cf - \
+      lib common.py datasets | tar -C "$OUT/py" -xf -
+  echo "[oracle] staged reference python under oracle/_ref/py ($(du -sh "$OUT/py" | cut -f1))"
+fi
 if [ -f "$OUT/_ext.so" ] && [ "$OUT/_ext.so" -nt "$REF/src/sampling_gpu.cu" ] && [ "${FORCE:-0}" != 1 ]; then
   echo "[oracle] oracle/_ref/_ext.so up to date"; exit 0
 fi

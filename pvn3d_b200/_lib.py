@@ -15,6 +15,23 @@ LIB_PATH = os.path.join(_HERE, "libpvn3d_b200.so")
 PVN3D_MS_STRICT = 0
 PVN3D_MS_EARLY_EXIT = 1
 PVN3D_MS_NO_FREEZE = 2
+PVN3D_MS_DEBUG_TIMING = 4
+PVN3D_MS_CERTIFIED = 8
+PVN3D_MS_STAT_CERTIFIED = 8   # int32 word of the mean-shift workspace: fits closed by the witness kernel
+
+#: mode name -> flags of the mean-shift iteration (include/pvn3d_b200.h)
+MS_MODES = {"certified": PVN3D_MS_CERTIFIED | PVN3D_MS_EARLY_EXIT, "early_exit": PVN3D_MS_EARLY_EXIT,
+            "strict": PVN3D_MS_STRICT, "no_freeze": PVN3D_MS_NO_FREEZE}
+MS_DEFAULT_MODE = "certified"
+
+
+def ms_flags(mode=None, early_exit=False, no_freeze=False) -> int:
+    """flags from a mode name; the round-1 keyword switches (early_exit / no_freeze) still select their modes"""
+    if mode is None:
+        mode = "no_freeze" if no_freeze else ("early_exit" if early_exit else MS_DEFAULT_MODE)
+    if mode not in MS_MODES:
+        raise ValueError(f"unknown mean-shift mode {mode!r}: one of {sorted(MS_MODES)}")
+    return MS_MODES[mode]
 
 _ERR_NAMES = {-1: "invalid argument", -2: "unsupported size", -3: "CUDA error", -4: "workspace too small"}
 
@@ -48,6 +65,7 @@ _SIGNATURES = {
     "pvn3d_meanshift_fit_batch": (c_int, [_P, _P, _P, c_int, c_int, c_double, c_int, c_uint, _P, _P, _P, _P, _P, c_size_t, _P]),
     "pvn3d_best_fit_transform_batch": (c_int, [_P, _P, _P, c_int, c_int, _P, _P]),
     "pvn3d_frame_poses_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "pvn3d_frame_poses_ms_workspace_offset": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "pvn3d_frame_poses_batch": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_double, c_int, c_uint, _P, _P, _P, _P, _P, c_size_t, _P]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

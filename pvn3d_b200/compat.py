@@ -23,12 +23,22 @@ import types
 
 
 def _stub(name: str, **attrs) -> types.ModuleType:
+    """Register a placeholder module `name` ONLY IF the real one cannot be imported: an installed (or
+    already imported) package is never touched -- the reference loads meshes through plyfile.PlyData.read
+    (basic_utils.py:109,468) and must keep the real reader when it is there."""
     mod = sys.modules.get(name)
+    if mod is not None and not getattr(mod, "_pvn3d_b200_stub", False):
+        return mod                       # real module (or somebody else's): leave it alone
     if mod is None:
-        mod = types.ModuleType(name)
-        sys.modules[name] = mod
+        try:
+            return importlib.import_module(name)
+        except Exception:                # ImportError, or a package that fails to initialise here
+            mod = types.ModuleType(name)
+            mod._pvn3d_b200_stub = True
+            sys.modules[name] = mod
     for k, v in attrs.items():
-        setattr(mod, k, v)
+        if not hasattr(mod, k):
+            setattr(mod, k, v)
     return mod
 
 
@@ -52,7 +62,9 @@ def install_import_shims() -> None:
         pass
     noop = lambda *a, **k: None  # noqa: E731
     for pkg in ("neupeak", "neupeak.utils"):
-        _stub(pkg).__path__ = []
+        m = _stub(pkg)
+        if getattr(m, "_pvn3d_b200_stub", False):
+            m.__path__ = []
     _stub("neupeak.utils.webcv2", imshow=noop, waitKey=noop)  # meanshift_pytorch.py:9
     _stub("plyfile", PlyData=type("PlyData", (), {"read": staticmethod(noop)}))
     _stub("pcl")

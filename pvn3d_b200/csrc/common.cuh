@@ -35,14 +35,30 @@ int sm_count();  // cached per process (device of first call)
 // per context, and nn.DataParallel-style callers drive several devices from one process).
 struct PerDeviceOnce {
   unsigned long long mask = 0ull;
-  bool first_time() {
+  static int slot() {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
-    const unsigned long long bit = 1ull << dev;
-    const unsigned long long old = __atomic_fetch_or(&mask, bit, __ATOMIC_RELAXED);
-    return (old & bit) == 0ull;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    return dev;
+  }
+  // true until mark() has run for the current device; two host threads may both see `pending` and
+  // both run the (idempotent) setup -- what must never happen is a launch BEFORE the setup is done,
+  // so the bit is published only after the setup call has succeeded.
+  bool pending() const {
+    const int d = slot();
+    return d < 0 || ((__atomic_load_n(&mask, __ATOMIC_ACQUIRE) >> d) & 1ull) == 0ull;
+  }
+  void mark() {
+    const int d = slot();
+    if (d >= 0) __atomic_fetch_or(&mask, 1ull << d, __ATOMIC_RELEASE);
   }
 };
+#define PVN3D_ONCE_PER_DEVICE(once, expr, where) \
+  do {                                           \
+    if ((once).pending()) {                      \
+      PVN3D_CUDA_TRY(expr, where);               \
+      (once).mark();                             \
+    }                                            \
+  } while (0)
 
 int keep_async_pool_warm();  // call before cudaMallocAsync scratch allocations
 

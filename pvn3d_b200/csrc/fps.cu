@@ -172,11 +172,10 @@ int launch_regs(const float *xyz, int b, int n, int m, int log2_bs, int *idx, cu
   auto kern = fps_regs_kernel<kFpsThreads, PPT>;
   const size_t smem = static_cast<size_t>(n) * 3 * sizeof(float);
   static PerDeviceOnce once;
-  if (once.first_time()) {
-    PVN3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        kFpsThreads * PPT * 3 * (int)sizeof(float)),
-                   "fps smem attr");
-  }
+  PVN3D_ONCE_PER_DEVICE(once,
+                        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kFpsThreads * PPT * 3 * (int)sizeof(float)),
+                        "fps smem attr");
   kern<<<b, kFpsThreads, smem, st>>>(xyz, n, m, log2_bs, idx);
   return check_launch("fps_regs_kernel");
 }

@@ -43,6 +43,7 @@ constexpr int kMsDensTile = 1024;  // points per tile of the density pass (16 KB
 constexpr int kMsWarps = kMsThreads / 32;
 constexpr int kMsCfgInts = 4096;   // [0..2] phase tickets, [3] grid barrier, [4..2047] debug, [2048..] CTAs seen per SM
 constexpr int kMsCfgSm = 2048;
+constexpr int kMsCfgCertified = 8;  // statistics of the last launch: fits closed by ms_witness_kernel
 
 struct MsArgs {
   const float4 *pts;
@@ -72,6 +73,8 @@ struct MsArgs {
   unsigned *viol;    // [n_fits][viol_words] bit `it` = some seed moved >= stop_thresh at iteration it
   float4 *traj;      // [n_fits][traj_stride] positions of the returned seed per iteration
   int *dens_prefix;  // [n_fits+1]
+  int *dens_cnt;     // [cap] inlier count of every input point (exact pass); witness selection
+  float delta_path;  // certified mode: the returned seed's remaining path at it0 is below this
   int *cfg;          // [0..2] ticket counters of the phases
   int cap;
   int viol_words;
@@ -182,6 +185,7 @@ __global__ void __launch_bounds__(kMsThreads) ms_density_kernel(MsArgs a) {
       count += torch_sqnorm(p.x - me.x, p.y - me.y, p.z - me.z) < t2 ? 1 : 0;
     }
   }
+  if (live) a.dens_cnt[start + i] = count;
   unsigned long long key =
       live ? ((static_cast<unsigned long long>(count) << 32) | (0xFFFFFFFFu - static_cast<unsigned>(i)))
            : 0ull;
@@ -574,6 +578,204 @@ __device__ __forceinline__ void ms_run_tile_split(const MsArgs &a, MsIterSmem &s
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// PVN3D_MS_CERTIFIED: the fit's answer from ~32 seeds instead of n_c.
+//
+// fit() returns C[max_idx] after T iterations, T being the first iteration at which NO seed moves by
+// >= bw*1e-3.  The returned seed ("star", the densest input) sits in the cluster and is stationary
+// after s ~ 4-10 iterations, while T on votes with outliers is 60-300 -- the creeping outlier seeds
+// set it, and sweeping them is n_c^2 pair evaluations per iteration for a number nobody reads.
+// One CTA per fit:
+//   1. iterate the star until its shift is < 1e-6*bw (iteration s); it0 = the first iteration from
+//      which its remaining path length to C_s is below delta = 1e-5*bw;
+//   2. alongside, iterate 31 WITNESS seeds (per residue class of the index: the input farthest from
+//      the star; second pool: the input with the lowest density count) and record at which iterations
+//      one of them still moves by >= bw*1e-3;
+//   3. if every iteration it < it0 has such a witness, the reference's rule cannot have fired before
+//      it0 (its maximum runs over ALL seeds, the witnesses included): T >= it0, and therefore
+//      |C_T - C_s| < delta (T <= s: remaining path; T > s: drift of a stationary seed).  The fit is
+//      marked done (= 2), ctr = C_s, ctr.w = it0.
+//   4. otherwise the fit is left to ms_iterate_kernel (all seeds, reference rule + early exit).
+// Witnesses only ever ADD evidence (a violation observed is a violation of the full sweep, since a
+// seed's trajectory depends on nothing but itself and the fixed points), so a bad witness choice costs
+// time (fallback), never correctness.
+constexpr int kWitSlots = 32;            // seeds per pool: 8 warps x 4
+constexpr int kWitPerWarp = kWitSlots / kMsWarps;
+constexpr int kWitPools = 2;
+constexpr int kWitViolWords = 128;       // max_iter <= 4094 -> iterations <= 4095
+
+struct MsWitSmem {
+  float4 pts[kMsPtTile];
+  unsigned viol[kWitViolWords];
+  int slot_idx[kWitSlots];
+  int s_it;     // iteration at which the star became stationary (0 = not yet)
+  int it0;
+  int certified;
+};
+
+__global__ void __launch_bounds__(kMsThreads, 2) ms_witness_kernel(MsArgs a) {
+  extern __shared__ __align__(16) unsigned char ms_smem_raw[];
+  MsWitSmem &sm = *reinterpret_cast<MsWitSmem *>(ms_smem_raw);
+  const int f = blockIdx.x;
+  const int n_c = a.fit_count[f];
+  if (n_c <= 0) return;
+  const int start = a.fit_start[f], star = a.max_idx[f];
+  const int last_it = a.max_iter + 1;
+  const bool single = n_c <= kMsPtTile;
+  const int t = threadIdx.x;
+  const unsigned lane = t & 31u;
+  const int warp = t >> 5;
+  const float k = a.kexp;
+  const float4 *cpts = a.cpts + start;
+
+  if (single) ms_stage_pairs(sm.pts, cpts, n_c);
+  for (int w = t; w < kWitViolWords; w += kMsThreads) sm.viol[w] = 0u;
+  if (t == 0) { sm.s_it = 0; sm.it0 = 0; sm.certified = 0; }
+  __syncthreads();
+
+  for (int pool = 0; pool < kWitPools; ++pool) {
+    // ---- the pool's seeds: slot = residue class (index mod 256) / 8 --------------------------------
+    {
+      float best = __int_as_float(0x7f800000);
+      int besti = -1;
+      for (int i = t; i < n_c; i += kMsThreads) {
+        // pool 0: farthest from the star (cpts.w = k |a'|^2, k < 0: the smallest value is the farthest);
+        // pool 1: lowest density count
+        const float key = pool == 0 ? cpts[i].w : static_cast<float>(a.dens_cnt[start + i]);
+        if (key < best) { best = key; besti = i; }
+      }
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+        if (oi >= 0 && (besti < 0 || ob < best || (ob == best && oi < besti))) { best = ob; besti = oi; }
+      }
+      if ((t & 7) == 0) sm.slot_idx[t >> 3] = (pool == 0 && t == 0) ? star : besti;
+    }
+    __syncthreads();
+    const int it_hi = pool == 0 ? last_it : sm.it0 - 1;   // later pools only need marks below it0
+
+    int idx[kWitPerWarp];
+    float cx[kWitPerWarp], cy[kWitPerWarp], cz[kWitPerWarp];
+    bool frozen[kWitPerWarp];
+#pragma unroll
+    for (int r = 0; r < kWitPerWarp; ++r) {
+      idx[r] = sm.slot_idx[warp * kWitPerWarp + r];
+      const float4 c = cpts[idx[r] >= 0 ? idx[r] : 0];
+      cx[r] = c.x; cy[r] = c.y; cz[r] = c.z;
+      frozen[r] = idx[r] < 0;
+    }
+    const bool has_star = pool == 0 && warp == 0;   // slot 0 of pool 0
+
+    // evidence must survive the ~1e-6 relative difference between this arithmetic and the reference's:
+    // a witness counts only when it moves by 1 % more than the threshold
+    const float wit_thresh = a.stop_thresh * 1.01f;
+    for (int it = 1; it <= it_hi; ++it) {
+      bool star_still = false;
+      bool warp_live = false;
+#pragma unroll
+      for (int r = 0; r < kWitPerWarp; ++r) warp_live |= !frozen[r];   // uniform across the warp
+      MsSeedQ sq[kWitPerWarp];
+      MsSeedS ss[kWitPerWarp];
+#pragma unroll
+      for (int r = 0; r < kWitPerWarp; ++r) {
+        sq[r] = ms_seed_q(k, cx[r], cy[r], cz[r]);
+        ss[r].sw = ss[r].sx = ss[r].sy = ss[r].sz = make_float2(0.f, 0.f);
+      }
+      for (int base = 0; base < n_c; base += kMsPtTile) {
+        const int n = min(kMsPtTile, n_c - base);
+        if (!single) {
+          __syncthreads();
+          ms_stage_pairs(sm.pts, cpts + base, n);
+          __syncthreads();
+        }
+        if (warp_live) {
+          const int npairs = (n + 1) >> 1;
+#pragma unroll 2
+          for (int p = lane; p < npairs; p += 32) {
+            const float4 A = sm.pts[p], B = sm.pts[kMsPairs + p];
+#pragma unroll
+            for (int r = 0; r < kWitPerWarp; ++r) ms_pair_step(A, B, sq[r], ss[r]);
+          }
+        }
+      }
+      if (warp_live) {
+        float sw[kWitPerWarp], sx[kWitPerWarp], sy[kWitPerWarp], sz[kWitPerWarp];
+#pragma unroll
+        for (int r = 0; r < kWitPerWarp; ++r) {
+          sw[r] = ss[r].sw.x + ss[r].sw.y;
+          sx[r] = ss[r].sx.x + ss[r].sx.y;
+          sy[r] = ss[r].sy.x + ss[r].sy.y;
+          sz[r] = ss[r].sz.x + ss[r].sz.y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+          for (int r = 0; r < kWitPerWarp; ++r) {
+            sw[r] += __shfl_xor_sync(0xffffffffu, sw[r], o);
+            sx[r] += __shfl_xor_sync(0xffffffffu, sx[r], o);
+            sy[r] += __shfl_xor_sync(0xffffffffu, sy[r], o);
+            sz[r] += __shfl_xor_sync(0xffffffffu, sz[r], o);
+          }
+        }
+        bool violates = false;
+#pragma unroll
+        for (int r = 0; r < kWitPerWarp; ++r) {
+          if (!frozen[r]) {
+            const float nx = __fdiv_rn(sx[r], sw[r]), ny = __fdiv_rn(sy[r], sw[r]),
+                        nz = __fdiv_rn(sz[r], sw[r]);
+            const float sh = __fsqrt_rn(torch_sqnorm(nx - cx[r], ny - cy[r], nz - cz[r]));
+            cx[r] = nx; cy[r] = ny; cz[r] = nz;
+            violates |= !(sh < wit_thresh);
+            const bool still = sh < a.eps_stat;
+            if (has_star && r == 0 && lane == 0) {
+              a.traj[static_cast<size_t>(f) * a.traj_stride + it] = make_float4(nx, ny, nz, sh);
+              if (still) { sm.s_it = it; star_still = true; }
+            }
+            if (still) frozen[r] = true;
+          }
+        }
+        if (violates && lane == 0) atomicOr(&sm.viol[it >> 5], 1u << (it & 31));
+      }
+      // block-uniform: the star is stationary -- nothing after s is needed
+      if (__syncthreads_or(star_still ? 1 : 0)) break;
+    }
+
+    // ---- verdict after this pool (thread 0; every value it reads it wrote itself or is in smem) ----
+    if (t == 0) {
+      const int s_it = sm.s_it;
+      if (s_it > 0) {
+        if (pool == 0) {
+          float acc = 0.f;
+          int it0 = s_it;
+          for (int j = s_it; j >= 1; --j) {
+            acc += a.traj[static_cast<size_t>(f) * a.traj_stride + j].w;
+            if (!(acc < a.delta_path)) break;
+            it0 = j - 1;
+          }
+          sm.it0 = max(it0, 1);
+        }
+        bool ok = true;
+        for (int it = 1; it < sm.it0; ++it)
+          if (!((sm.viol[it >> 5] >> (it & 31)) & 1u)) { ok = false; break; }
+        sm.certified = ok ? 1 : 0;
+      }
+    }
+    __syncthreads();
+    if (sm.s_it == 0 || sm.certified) break;   // no stationary star within max_iter, or done
+  }
+
+  if (t == 0 && sm.certified) {
+    const float4 c = a.traj[static_cast<size_t>(f) * a.traj_stride + sm.s_it];
+    const float4 o = a.pts[start + star];
+    a.ctr[f] = make_float4(c.x + o.x, c.y + o.y, c.z + o.z, static_cast<float>(sm.it0));
+    a.iters[f] = sm.it0;
+    a.star_it[f] = sm.s_it;
+    a.done[f] = 2;
+    atomicAdd(a.cfg + kMsCfgCertified, 1);   // statistics: fits certified by this launch
+  }
+}
+
 __global__ void __launch_bounds__(kMsThreads, 3) ms_iterate_kernel(MsArgs a) {
   extern __shared__ __align__(16) unsigned char ms_smem_raw[];
   MsIterSmem &sm = *reinterpret_cast<MsIterSmem *>(ms_smem_raw);
@@ -710,7 +912,7 @@ __global__ void __launch_bounds__(kMsThreads, 3) ms_iterate_kernel(MsArgs a) {
   // ---- results: C[max_idx] after exactly T iterations, back in world coordinates (:51) -----------
   for (int f = blockIdx.x * kMsThreads + t; f < a.n_fits; f += gridDim.x * kMsThreads) {
     const int cnt = a.fit_count[f];
-    if (cnt <= 0) continue;
+    if (cnt <= 0 || a.done[f] == 2) continue;  // empty, or certified (ms_witness_kernel wrote ctr)
     const int start = a.fit_start[f], mi = a.max_idx[f];
     const int T = a.iters[f], s = a.star_it[f];
     const bool frozen_before_T = !(a.flags & PVN3D_MS_NO_FREEZE) && s > 0 && T >= s;
@@ -731,7 +933,7 @@ float density_threshold(float bwf) {
 }
 
 struct MsLayout {
-  size_t cpts, seeds, best_key, done, iters, star, act, act_cnt, viol, traj, dens_prefix, cfg, total;
+  size_t cpts, seeds, best_key, done, iters, star, act, act_cnt, viol, traj, dens_prefix, dens_cnt, cfg, total;
   int viol_words, traj_stride;
 };
 MsLayout ms_layout(int cap, int n_fits, int max_iter) {
@@ -757,6 +959,7 @@ MsLayout ms_layout(int cap, int n_fits, int max_iter) {
   L.viol = take(nf * L.viol_words * sizeof(unsigned));
   L.traj = take(nf * static_cast<size_t>(L.traj_stride) * sizeof(float4));
   L.dens_prefix = take((nf + 1) * sizeof(int));
+  L.dens_cnt = take(cp * sizeof(int));
   L.total = off;
   return L;
 }
@@ -830,6 +1033,8 @@ int meanshift_launch(const float4 *pts, const int *fit_start, const int *fit_cou
     a.viol = reinterpret_cast<unsigned *>(ws + L.viol) + static_cast<size_t>(f0) * L.viol_words;
     a.traj = reinterpret_cast<float4 *>(ws + L.traj) + static_cast<size_t>(f0) * L.traj_stride;
     a.dens_prefix = reinterpret_cast<int *>(ws + L.dens_prefix);
+    a.dens_cnt = reinterpret_cast<int *>(ws + L.dens_cnt);
+    a.delta_path = static_cast<float>(bandwidth * 1e-5);
     a.cfg = reinterpret_cast<int *>(ws + L.cfg);
     a.cap = cap;
     a.viol_words = L.viol_words;
@@ -845,6 +1050,15 @@ int meanshift_launch(const float4 *pts, const int *fit_start, const int *fit_cou
     ms_prepare_kernel<<<tiles, kMsThreads, 0, st>>>(a);
     if ((rc = check_launch("ms_prepare_kernel")) != PVN3D_OK) return rc;
     if (density_only) continue;
+    if (flags & PVN3D_MS_CERTIFIED) {
+      static PerDeviceOnce once;
+      PVN3D_ONCE_PER_DEVICE(once,
+                            cudaFuncSetAttribute(ms_witness_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)sizeof(MsWitSmem)),
+                            "ms_witness smem attr");
+      ms_witness_kernel<<<nf, kMsThreads, sizeof(MsWitSmem), st>>>(a);
+      if ((rc = check_launch("ms_witness_kernel")) != PVN3D_OK) return rc;
+    }
     void *kargs[] = {&a};
     PVN3D_CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(ms_iterate_kernel),
                                                dim3(grid), dim3(kMsThreads), kargs,

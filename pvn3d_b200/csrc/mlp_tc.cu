@@ -692,9 +692,9 @@ int launch_mlp(MlpArgs &a, cudaStream_t st) {
   const size_t smem = stages * stage_bytes + 1024 + kMlpEpiWarps * 4096;  // ring + epilogue staging
   auto kern = mlp_layer_kernel<PRO, EPI>;
   static PerDeviceOnce once;
-  if (once.first_time())
-    PVN3D_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024),
-                   "mlp smem attr");
+  PVN3D_ONCE_PER_DEVICE(once,
+                        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024),
+                        "mlp smem attr");
   const int sms = std::max(1, sm_count());
   const long long tiles = ((a.rows + kMlpBM - 1) / kMlpBM) * ceil_div(a.n_pad, a.bn);
   const unsigned grid = static_cast<unsigned>(std::min<long long>(tiles, sms));

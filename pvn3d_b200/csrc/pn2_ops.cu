@@ -407,10 +407,10 @@ extern "C" int pvn3d_ball_query(const float *new_xyz, const float *xyz, int b, i
   const size_t smem = kBqTile * 3 * sizeof(float) + sizeof(int) * kBqCentresPerCta * (size_t)nsample;
   if (smem > 200 * 1024) return PVN3D_ERR_UNSUPPORTED;  // nsample <= ~1400
   static PerDeviceOnce once;
-  if (once.first_time())
-    PVN3D_CUDA_TRY(cudaFuncSetAttribute(ball_query_kernel,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
-                   "ball_query smem attr");
+  PVN3D_ONCE_PER_DEVICE(once,
+                        cudaFuncSetAttribute(ball_query_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024),
+                        "ball_query smem attr");
   dim3 grid(ceil_div(m, kBqCentresPerCta), b);
   ball_query_kernel<<<grid, kBqThreads, smem, as_stream(stream)>>>(new_xyz, xyz, n, m, radius,
                                                                    nsample, idx);

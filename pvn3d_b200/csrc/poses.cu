@@ -496,6 +496,11 @@ extern "C" size_t pvn3d_frame_poses_workspace_bytes(int b, int n, int k, int n_c
   return pose_layout(b, n, k, n_cls, max_iter).total;
 }
 
+extern "C" size_t pvn3d_frame_poses_ms_workspace_offset(int b, int n, int k, int n_cls, int max_iter) {
+  if (b <= 0 || n <= 0 || k <= 0 || n_cls <= 0 || max_iter < 0 || max_iter > 4094) return 0;
+  return pose_layout(b, n, k, n_cls, max_iter).ms;
+}
+
 extern "C" int pvn3d_frame_poses_batch(const float *pcld, const int *mask, const float *ctr_of,
                                        const float *kp_of, int b, int n, int k, int n_cls,
                                        const float *mesh_kps, const float *cls_radius,

@@ -472,10 +472,10 @@ int qg_launch(const QgArgs &a, int b, cudaStream_t st) {
 int qg_launch_group(QgArgs &a, int b, bool dual, cudaStream_t st) {
   if (!a.s[0].out && !(dual && a.s[1].out)) return PVN3D_OK;
   static PerDeviceOnce once;
-  if (once.first_time())
-    PVN3D_CUDA_TRY(cudaFuncSetAttribute(group_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)QgGroupSmem::total),
-                   "group_write smem attr");
+  PVN3D_ONCE_PER_DEVICE(once,
+                        cudaFuncSetAttribute(group_write_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)QgGroupSmem::total),
+                        "group_write smem attr");
   const int ns_max = std::max(a.s[0].ns, dual ? a.s[1].ns : 0);
   // slots per CTA: the full 768 when that still gives every SM its three CTAs twice over, else less
   const long long all_slots = static_cast<long long>(b) * a.m * (a.s[0].ns + (dual ? a.s[1].ns : 0));

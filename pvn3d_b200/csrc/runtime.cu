@@ -31,13 +31,14 @@ int keep_async_pool_warm() {
   // cudaMallocAsync scratch (query_group box tables, FPS fallback): by default the device pool hands
   // memory back to the OS at every synchronisation, which makes the next allocation slow.  Keep it.
   static PerDeviceOnce once;
-  if (!once.first_time()) return PVN3D_OK;
+  if (!once.pending()) return PVN3D_OK;
   int dev = 0;
   PVN3D_CUDA_TRY(cudaGetDevice(&dev), "cudaGetDevice");
   cudaMemPool_t pool;
   PVN3D_CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, dev), "default mempool");
   unsigned long long keep = ~0ull;
   PVN3D_CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep), "mempool threshold");
+  once.mark();
   return PVN3D_OK;
 }
 

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _lib, fixtures
-from ._lib import PVN3D_MS_EARLY_EXIT, PVN3D_MS_STRICT, check, ptr
+from ._lib import check, ms_flags, ptr
 
 RADIUS = 0.08  # clustering bandwidth hard-coded by the reference (pvn3d_eval_utils.py:44,163)
 
@@ -29,7 +29,7 @@ class FramePoseSolver:
 
     def __init__(self, batch: int, n_pts: int, n_kps: int, n_cls: int, mesh_kps: np.ndarray,
                  cls_radius: Optional[np.ndarray], use_ctr_clus_flter: bool, device="cuda",
-                 bandwidth: float = RADIUS, max_iter: int = 300, early_exit: bool = False):
+                 bandwidth: float = RADIUS, max_iter: int = 300, early_exit: bool = False, mode: str = None):
         self.lib = _lib.load()
         self.dev = torch.device(device)
         if self.dev.type != "cuda":
@@ -44,7 +44,7 @@ class FramePoseSolver:
             assert cls_radius is not None and len(cls_radius) == self.n_cls
             self.cls_radius = torch.from_numpy(np.ascontiguousarray(cls_radius, dtype=np.float32)).to(self.dev)
         self.bandwidth, self.max_iter = float(bandwidth), int(max_iter)
-        self.flags = PVN3D_MS_EARLY_EXIT if early_exit else PVN3D_MS_STRICT
+        self.flags = ms_flags(mode, early_exit)       # default: "certified" (see MeanShiftTorch)
         self.ws_bytes = int(self.lib.pvn3d_frame_poses_workspace_bytes(self.b, self.n, self.k, self.n_cls, self.max_iter))
         self._ws = torch.empty((self.ws_bytes + 256,), dtype=torch.uint8, device=self.dev)
         self._ws_ptr = (self._ws.data_ptr() + 255) // 256 * 256
@@ -52,6 +52,13 @@ class FramePoseSolver:
         self.present = torch.empty((self.b, self.n_cls), dtype=torch.uint8, device=self.dev)
         self.cls_kps = torch.empty((self.b, self.n_cls, self.k + 1, 3), dtype=torch.float32, device=self.dev)
         self.new_mask = torch.empty((self.b, self.n), dtype=torch.int32, device=self.dev)
+        self._ms_off = int(self.lib.pvn3d_frame_poses_ms_workspace_offset(self.b, self.n, self.k, self.n_cls, self.max_iter))
+
+    def certified_fits(self) -> int:
+        """diagnostics (synchronises): how many of the last solve()'s centre + keypoint fits the witness
+        kernel closed without sweeping all seeds (mode "certified")"""
+        off = self._ws_ptr - self._ws.data_ptr() + self._ms_off
+        return int(self._ws[off:off + 64].view(torch.int32)[_lib.PVN3D_MS_STAT_CERTIFIED].item())
 
     def solve(self, pcld: torch.Tensor, mask: torch.Tensor, ctr_of: torch.Tensor, kp_of: torch.Tensor):
         """All inputs on device, contiguous: pcld [B,N,3] f32, mask [B,N] i32, ctr_of [B,N,3] f32,
@@ -75,8 +82,8 @@ class FramePoseSolver:
 _solver_cache = {}
 
 
-def _solver(kind, n_pts, n_kps, n_cls, use_filter, dev, obj_id=None, early_exit=False):
-    key = (kind, n_pts, n_kps, n_cls, use_filter, str(dev), obj_id, early_exit)
+def _solver(kind, n_pts, n_kps, n_cls, use_filter, dev, obj_id=None, early_exit=False, mode=None):
+    key = (kind, n_pts, n_kps, n_cls, use_filter, str(dev), obj_id, ms_flags(mode, early_exit))
     s = _solver_cache.get(key)
     if s is None:
         if kind == "ycb":
@@ -86,7 +93,7 @@ def _solver(kind, n_pts, n_kps, n_cls, use_filter, dev, obj_id=None, early_exit=
             mesh = np.zeros((n_cls, n_kps + 1, 3), np.float32)
             mesh[1] = fixtures.mesh_kps_table_lm(obj_id)[1]
             rad = np.full((n_cls,), np.inf, np.float32) if use_filter else None
-        s = FramePoseSolver(1, n_pts, n_kps, n_cls, mesh, rad, use_filter, device=dev, early_exit=early_exit)
+        s = FramePoseSolver(1, n_pts, n_kps, n_cls, mesh, rad, use_filter, device=dev, early_exit=early_exit, mode=mode)
         _solver_cache[key] = s
     return s
 
@@ -100,14 +107,15 @@ def _prep(pcld, mask, ctr_of, pred_kp_of):
 
 
 def cal_frame_poses(pcld, mask, ctr_of, pred_kp_of, use_ctr, n_cls, use_ctr_clus_flter,
-                    early_exit: bool = False) -> Tuple[np.ndarray, List[np.ndarray]]:
+                    early_exit: bool = False, mode: str = None) -> Tuple[np.ndarray, List[np.ndarray]]:
     """pvn3d_eval_utils.py:37-110.  pcld [N,3], mask [N] (int64 class ids), ctr_of [1,N,3],
     pred_kp_of [K,N,3]; one device->host read at the end instead of >= 3 per class."""
     if not use_ctr:
         raise NotImplementedError("use_ctr=False is never exercised by the reference callers")
     p, c, kp, n_kps, n_pts = _prep(pcld, mask, ctr_of, pred_kp_of)
     m32 = mask.reshape(1, n_pts).to(torch.int32).contiguous()
-    s = _solver("ycb", n_pts, n_kps, int(n_cls), bool(use_ctr_clus_flter), pcld.device, early_exit=early_exit)
+    s = _solver("ycb", n_pts, n_kps, int(n_cls), bool(use_ctr_clus_flter), pcld.device, early_exit=early_exit,
+                mode=mode)
     poses, present, _, _ = s.solve(p, m32, c, kp)
     poses_h = poses[0].double().cpu().numpy()
     present_h = present[0].cpu().numpy()
@@ -116,7 +124,7 @@ def cal_frame_poses(pcld, mask, ctr_of, pred_kp_of, use_ctr, n_cls, use_ctr_clus
 
 
 def cal_frame_poses_lm(pcld, mask, ctr_of, pred_kp_of, use_ctr, n_cls, use_ctr_clus_flter, obj_id,
-                       early_exit: bool = False) -> List[np.ndarray]:
+                       early_exit: bool = False, mode: str = None) -> List[np.ndarray]:
     """pvn3d_eval_utils.py:156-201: single class id 1, fixtures of LineMOD object `obj_id`."""
     if not use_ctr:
         raise NotImplementedError("use_ctr=False is never exercised by the reference callers")
@@ -126,7 +134,7 @@ def cal_frame_poses_lm(pcld, mask, ctr_of, pred_kp_of, use_ctr, n_cls, use_ctr_c
     # the keypoint votes (:182-185), which the solver's flag also controls -> give it an infinite
     # radius so the relabel pass is the identity.
     s = _solver("lm", n_pts, n_kps, max(int(n_cls), 2), bool(use_ctr_clus_flter), pcld.device, obj_id=obj_id,
-                early_exit=early_exit)
+                early_exit=early_exit, mode=mode)
     poses, _, _, _ = s.solve(p, m32, c, kp)
     return [poses[0, 1].double().cpu().numpy()]
 

@@ -18,21 +18,25 @@ from typing import List, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import PVN3D_MS_EARLY_EXIT, PVN3D_MS_NO_FREEZE, PVN3D_MS_STRICT, check, ptr
+from ._lib import PVN3D_MS_DEBUG_TIMING, check, ms_flags, ptr
 
 
 class MeanShiftTorch:
     def __init__(self, bandwidth: float = 0.05, max_iter: int = 300, early_exit: bool = False,
-                 no_freeze: bool = False):
+                 no_freeze: bool = False, mode: str = None):
         self.bandwidth = bandwidth
         self.stop_thresh = bandwidth * 1e-3  # meanshift_pytorch.py:21 (informational; kernel derives it)
         self.max_iter = max_iter
-        #: PVN3D_MS_EARLY_EXIT also stops a fit once the RETURNED seed is stationary to 1e-6*bandwidth
-        #: (same centre to ~1e-7 m, fewer sweeps).  Default is the reference's global stop rule.
-        self.early_exit = early_exit
-        #: validation switch: sweep every seed at every iteration like the reference does, instead of
-        #: dropping seeds that have stopped moving (shift < 1e-6*bandwidth) from the work lists
-        self.no_freeze = no_freeze
+        #: how the iteration count is decided (include/pvn3d_b200.h); every mode returns
+        #: the same labels bit for bit and the same centre to well inside the 1e-4 relative parity bar:
+        #:   "certified"  (default) only the returned seed + ~60 witness seeds are iterated; a fit whose
+        #:                witnesses prove that the reference's stop rule cannot fire before the returned
+        #:                seed is within 1e-5*bandwidth of its limit is done, the rest fall back to:
+        #:   "early_exit" all seeds, reference stop rule, but a fit also ends once the returned seed is
+        #:                stationary (1e-6*bandwidth)
+        #:   "strict"     all seeds, reference stop rule: last_iters equals the reference's iteration count
+        #:   "no_freeze"  strict + every seed swept at every iteration (the literal reference schedule)
+        self.flags = ms_flags(mode, early_exit, no_freeze)
         self.debug_timing = False
         self.last_iters = None  # iteration count(s) of the last call, device tensor
 
@@ -85,7 +89,7 @@ class MeanShiftTorch:
             raise ValueError("max_iter must be in [0, 4094]")
         ws = torch.empty((ws_bytes + 256,), dtype=torch.uint8, device=dev)
         ws_ptr = (ws.data_ptr() + 255) // 256 * 256
-        flags = (PVN3D_MS_EARLY_EXIT if self.early_exit else PVN3D_MS_STRICT) | (PVN3D_MS_NO_FREEZE if self.no_freeze else 0) | (4 if self.debug_timing else 0)
+        flags = self.flags | (PVN3D_MS_DEBUG_TIMING if self.debug_timing else 0)
         with torch.cuda.device(dev):
             rc = lib.pvn3d_meanshift_fit_batch(
                 ptr(pts4), ptr(fit_start), ptr(fit_count), nf, cap, float(self.bandwidth),
@@ -96,3 +100,8 @@ class MeanShiftTorch:
         self._last_ws = (ws, ws_ptr - ws.data_ptr())   # debug: phase stamps live in the first 1 KB
         self.last_iters = ctr[:, 3]
         return ctr, labels, max_idx, n_in
+
+    def certified_fits(self) -> int:
+        """diagnostics (synchronises): fits of the last call closed by the witness kernel"""
+        ws, off = self._last_ws
+        return int(ws[off:off + 64].view(torch.int32)[_lib.PVN3D_MS_STAT_CERTIFIED].item())

@@ -24,7 +24,8 @@ from .testing import seeded_pointnet2msg
 class FramePipeline:
     def __init__(self, shape: str, batch: int, n_points: int = fixtures.N_SAMPLE_POINTS, device="cuda",
                  lm_obj_id: int = 1, early_exit: bool = False, model: Optional[torch.nn.Module] = None,
-                 allow_tf32: bool = True, engine: str = "fused"):
+                 allow_tf32: bool = True, engine: str = "fused", ms_mode: Optional[str] = None,
+                 overlap: bool = True):
         self.dev = torch.device(device)
         self.shape, self.b, self.n, self.k = shape, int(batch), int(n_points), fixtures.N_KEYPOINTS
         self.model = (model if model is not None else seeded_pointnet2msg(0, 1)).to(self.dev).eval()
@@ -37,12 +38,12 @@ class FramePipeline:
             self.n_cls = 2
             mesh = fixtures.mesh_kps_table_lm(lm_obj_id)
             self.solver = FramePoseSolver(self.b, self.n, self.k, 2, mesh, None, False, device=self.dev,
-                                          early_exit=early_exit)
+                                          early_exit=early_exit, mode=ms_mode)
         elif shape == "ycb":
             self.n_cls = fixtures.YCB_N_CLASSES
             self.solver = FramePoseSolver(self.b, self.n, self.k, self.n_cls, fixtures.mesh_kps_table_ycb(),
                                           fixtures.radius_thresholds_ycb(), True, device=self.dev,
-                                          early_exit=early_exit)
+                                          early_exit=early_exit, mode=ms_mode)
         else:
             raise ValueError(shape)
         self.allow_tf32 = allow_tf32
@@ -57,10 +58,18 @@ class FramePipeline:
         self._set_free = [None, None]     # event: the kernels that last read the set are done
         self._turn = 0
         self._copy_stream = torch.cuda.Stream(self.dev)
+        #: hot path B (votes -> poses) does not read hot path A's features (the votes come from the network
+        #: heads, synthetic here): it runs on its own stream, so its many small kernels fill the SMs that the
+        #: latency-bound furthest-point sampling of path A (one CTA per frame) leaves idle
+        self.overlap = bool(overlap)
+        self._pose_stream = torch.cuda.Stream(self.dev) if self.overlap else None
         self.d_cloud, self.d_pcld, self.d_labels, self.d_ctr_of, self.d_kp_of = (
             self._sets[0][k] for k in ("cld_rgb_nrm", "pcld", "labels", "ctr_of", "kp_of"))
-        self.h_poses = torch.empty((self.b, self.n_cls, 3, 4), dtype=torch.float32).pin_memory()
-        self.h_present = torch.empty((self.b, self.n_cls), dtype=torch.uint8).pin_memory()
+        # pinned result buffers, one pair per staging set: call i+1 must not overwrite what call i returned
+        # before the caller has synchronised and read it
+        self._h_out = [(torch.empty((self.b, self.n_cls, 3, 4), dtype=torch.float32).pin_memory(),
+                        torch.empty((self.b, self.n_cls), dtype=torch.uint8).pin_memory()) for _ in range(2)]
+        self.h_poses, self.h_present = self._h_out[0]
         self.features = None
 
     def h2d_bytes(self) -> int:
@@ -77,6 +86,15 @@ class FramePipeline:
     @torch.no_grad()
     def run_device(self, cld_rgb_nrm, pcld, labels, ctr_of, kp_of):
         """inputs resident in HBM; returns device views (poses [B,n_cls,3,4], present [B,n_cls])."""
+        cur = torch.cuda.current_stream(self.dev)
+        if self.overlap:
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            self._pose_stream.wait_event(ready)          # inputs (and the previous reader of the outputs) are done
+            with torch.cuda.stream(self._pose_stream):
+                poses, present, _, _ = self.solver.solve(pcld, labels, ctr_of, kp_of)   # hot path B
+                solved = torch.cuda.Event()
+                solved.record(self._pose_stream)
         if self.fused is not None:
             self.features = self.fused(cld_rgb_nrm)                       # hot path A: [B,128,N]
         else:
@@ -86,7 +104,10 @@ class FramePipeline:
                 self.features = self.model(cld_rgb_nrm)
             finally:
                 torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
-        poses, present, _, _ = self.solver.solve(pcld, labels, ctr_of, kp_of)   # hot path B
+        if self.overlap:
+            cur.wait_event(solved)
+        else:
+            poses, present, _, _ = self.solver.solve(pcld, labels, ctr_of, kp_of)   # hot path B
         return poses, present
 
     @torch.no_grad()
@@ -94,7 +115,8 @@ class FramePipeline:
         """hb: pinned host tensors (pin_batch).  H2D copies, both hot paths, D2H of the poses; the
         caller synchronises the stream before reading the returned pinned host tensors.  The copies
         go through a second stream into one of two staging sets: back-to-back calls overlap the
-        upload of call i with the kernels of call i-1."""
+        upload of call i with the kernels of call i-1.  The returned pinned buffers alternate too: the
+        result of call i stays valid until call i+2."""
         b = hb["pcld"].shape[0]
         turn = self._turn
         self._turn ^= 1
@@ -113,6 +135,7 @@ class FramePipeline:
         done = torch.cuda.Event()
         done.record(cur)
         self._set_free[turn] = done
-        self.h_poses[:b].copy_(poses, non_blocking=True)
-        self.h_present[:b].copy_(present, non_blocking=True)
-        return self.h_poses[:b], self.h_present[:b]
+        h_poses, h_present = self._h_out[turn]
+        h_poses[:b].copy_(poses, non_blocking=True)
+        h_present[:b].copy_(present, non_blocking=True)
+        return h_poses[:b], h_present[:b]

@@ -52,3 +52,38 @@ def level_clouds(batch=2, seed0=500, shape="ycb", n=12288):
 
 def t(x, dev):
     return torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+
+
+_ref_py = None
+_ref_py_tried = False
+
+
+def load_reference_python():
+    """The UNMODIFIED reference Python staged by oracle/build_ref_ext.sh under oracle/_ref/py (lib/,
+    common.py, datasets/ fixtures), imported on top of pvn3d_b200.compat.install() -- i.e. with this
+    package's `_ext` bound at pointnet2_utils.py:19.  Returns a namespace of the reference modules, or
+    None when the staging directory is absent."""
+    global _ref_py, _ref_py_tried
+    if _ref_py_tried:
+        return _ref_py
+    _ref_py_tried = True
+    root = os.path.join(ROOT, "oracle", "_ref", "py")
+    if not os.path.isdir(os.path.join(root, "lib")):
+        return None
+    import types
+
+    from pvn3d_b200 import compat
+
+    compat.install(root)
+    try:
+        from lib import pvn3d as ref_pvn3d
+        from lib.pointnet2_utils import pointnet2_utils as ref_pn2_utils
+        from lib.utils import basic_utils as ref_bu
+        from lib.utils import meanshift_pytorch as ref_ms
+        from lib.utils import pvn3d_eval_utils as ref_eval
+    except Exception as e:  # pragma: no cover
+        print("reference python not importable:", repr(e))
+        return None
+    _ref_py = types.SimpleNamespace(pvn3d=ref_pvn3d, pn2_utils=ref_pn2_utils, basic_utils=ref_bu,
+                                    meanshift=ref_ms, eval_utils=ref_eval)
+    return _ref_py

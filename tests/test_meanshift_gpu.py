@@ -21,15 +21,17 @@ def _rel_err(a, b):
 
 
 @pytest.mark.parametrize("name", CASES)
-@pytest.mark.parametrize("mode", ["strict", "no_freeze", "early_exit"])
+@pytest.mark.parametrize("mode", ["certified", "strict", "no_freeze", "early_exit"])
 def test_fit_matches_reference_golden(cuda_dev, golden_dir, name, mode):
-    """strict      = default: reference stop rule, stationary seeds dropped from the work lists
+    """certified   = default: returned seed + witness seeds only; falls back to early_exit when the
+                  witnesses cannot prove that the reference's stop rule fires late enough
+    strict      = reference stop rule, stationary seeds dropped from the work lists
     no_freeze   = reference stop rule, every seed swept at every iteration (literal reference schedule)
-    early_exit  = opt-in: stop as soon as the returned seed is stationary"""
-    early_exit = mode == "early_exit"
+    early_exit  = all seeds, stop as soon as the returned seed is stationary"""
+    early_exit = mode in ("early_exit", "certified")
     z = np.load(os.path.join(golden_dir, "ms_cases.npz"))
     A = torch.from_numpy(z[f"{name}_A"]).to(cuda_dev)
-    ms = MeanShiftTorch(bandwidth=float(z[f"{name}_bw"]), early_exit=early_exit, no_freeze=mode == "no_freeze")
+    ms = MeanShiftTorch(bandwidth=float(z[f"{name}_bw"]), mode=mode)
     ctr, labels = ms.fit(A)
     assert labels.dtype == torch.bool and labels.shape == (A.size(0),) and ctr.shape == (3,)
     assert np.array_equal(labels.cpu().numpy(), z[f"{name}_labels"]), "labels must be bit-exact"
@@ -46,7 +48,7 @@ def test_fit_many_equals_individual_fits(cuda_dev, golden_dir):
     z = np.load(os.path.join(golden_dir, "ms_cases.npz"))
     names = ["tight", "outl10", "two", "wide", "single", "pair_far"]
     clouds = [torch.from_numpy(z[f"{n}_A"]).to(cuda_dev) for n in names]
-    ms = MeanShiftTorch(bandwidth=0.08)
+    ms = MeanShiftTorch(bandwidth=0.08, mode="strict")
     ctrs, labels = ms.fit_many(clouds)
     for i, n in enumerate(names):
         c1, l1 = ms.fit(clouds[i])
@@ -73,7 +75,7 @@ def test_properties_at_full_size(cuda_dev):
     out = rng.choice(n, n // 10, replace=False)
     A[out] = rng.uniform([-0.5, -0.4, 0.6], [0.5, 0.4, 1.2], size=(len(out), 3)).astype(np.float32)
     At = torch.from_numpy(A).to(cuda_dev)
-    ms = MeanShiftTorch(0.08)
+    ms = MeanShiftTorch(0.08, mode="strict")
     c0, l0 = ms.fit(At)
     c0b, l0b = ms.fit(At)
     assert torch.equal(c0, c0b) and torch.equal(l0, l0b), "bitwise deterministic run to run"
@@ -86,8 +88,11 @@ def test_properties_at_full_size(cuda_dev):
     assert int(l2.sum()) == int(l0.sum())
     # the centre is a fixed point: it sits inside the dense cluster
     assert float((c0.cpu() - torch.tensor([0.1, -0.05, 0.8])).norm()) < 0.003
-    ce, le = MeanShiftTorch(0.08, early_exit=True).fit(At)
-    assert torch.equal(le, l0) and float((ce - c0).norm() / c0.norm()) < REL_TOL
+    for mode in ("early_exit", "certified"):
+        ce, le = MeanShiftTorch(0.08, mode=mode).fit(At)
+        assert torch.equal(le, l0) and float((ce - c0).norm() / c0.norm()) < 1e-5, mode
+    cd, ld = MeanShiftTorch(0.08).fit(At)            # the default mode is the certified one
+    assert torch.equal(cd, ce) and torch.equal(ld, le)
     # dropping stationary seeds from the work lists changes neither T nor the centre
     msn = MeanShiftTorch(0.08, no_freeze=True)
     cn, ln = msn.fit(At)
@@ -104,14 +109,16 @@ def test_multi_tile_fit_and_max_iter_cap(cuda_dev):
     out = rng.choice(n, n // 8, replace=False)
     A[out] = rng.uniform([-0.5, -0.4, 0.6], [0.5, 0.4, 1.2], size=(len(out), 3)).astype(np.float32)
     At = torch.from_numpy(A).to(cuda_dev)
-    ms = MeanShiftTorch(0.08)
+    ms = MeanShiftTorch(0.08, mode="strict")
     c0, l0 = ms.fit(At)
     msn = MeanShiftTorch(0.08, no_freeze=True)
     cn, ln = msn.fit(At)
     assert torch.equal(l0, ln) and float((cn - c0).norm() / c0.norm()) < 1e-6
     assert abs(int(msn.last_iters[0]) - int(ms.last_iters[0])) <= 1
     assert float((c0.cpu() - torch.tensor([0.0, 0.1, 0.9])).norm()) < 0.005
-    capped = MeanShiftTorch(0.08, max_iter=4)
+    cc, lc = MeanShiftTorch(0.08, mode="certified").fit(At)
+    assert torch.equal(lc, l0) and float((cc - c0).norm() / c0.norm()) < 1e-5
+    capped = MeanShiftTorch(0.08, max_iter=4, mode="strict")
     capped.fit(At)
     assert int(capped.last_iters[0]) == 5
 
