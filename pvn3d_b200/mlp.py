@@ -160,6 +160,36 @@ class FusedPointnet2MSG:
                 prev_pad = pl.n_pad
                 layers.append(pl)
             self.fp.append(layers)
+        self._marks = None
+
+    def _m(self, family: str) -> None:
+        """profile(): close the interval since the previous mark and charge it to `family`"""
+        if self._marks is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._marks.append((family, e))
+
+    @torch.no_grad()
+    def profile(self, pointcloud: torch.Tensor, reps: int = 3) -> Dict[str, float]:
+        """One instrumented forward per repetition: CUDA events on the launching stream between the kernel
+        families (fps / ball / mlp / three_nn / glue); returns the median ms per family per call.  The
+        events serialise nothing that is not already serial (one stream)."""
+        import statistics
+
+        self.forward(pointcloud)
+        runs = []
+        for _ in range(reps):
+            torch.cuda.synchronize(self.dev)
+            self._marks = []
+            self._m("start")
+            self.forward(pointcloud)
+            marks, self._marks = self._marks, None
+            torch.cuda.synchronize(self.dev)
+            acc: Dict[str, float] = {}
+            for (_, e0), (fam, e1) in zip(marks[:-1], marks[1:]):
+                acc[fam] = acc.get(fam, 0.0) + e0.elapsed_time(e1)
+            runs.append(acc)
+        return {k: statistics.median(r.get(k, 0.0) for r in runs) for k in runs[0]}
 
     @torch.no_grad()
     def forward(self, pointcloud: torch.Tensor) -> torch.Tensor:
@@ -176,10 +206,13 @@ class FusedPointnet2MSG:
             x = l_xyz[-1]
             fptr, ldf, c_feat = feats[-1]
             fidx = _ext.furthest_point_sampling(x, npoint)
+            self._m("fps")
             new_xyz = torch.gather(x, 1, fidx.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
             out_l = torch.empty((b, npoint, self.sa_out[li]), dtype=torch.float32, device=self.dev)
             col = 0
+            self._m("glue")
             idxs = _ext.ball_query2(new_xyz, x, radii, nsamples)    # one pass over the cloud for both radii
+            self._m("ball")
             for (idx, ns, layers) in zip(idxs, nsamples, self.sa[li]):
                 # intermediates are stored TF32-rounded (what the next layer's operand is anyway)
                 h = mlp_sa_first(x, new_xyz, fptr, ldf, c_feat, idx, layers[0], round_out=True)
@@ -187,6 +220,7 @@ class FusedPointnet2MSG:
                     h = mlp_dense(h, mid, round_out=True, a_tf32=True)
                 mlp_dense(h, layers[-1], pool=ns, out=out_l.view(b * npoint, -1), col0=col, a_tf32=True)
                 col += layers[-1].n
+            self._m("mlp")
             l_xyz.append(new_xyz)
             feats.append((out_l.data_ptr(), out_l.size(-1), out_l.size(-1)))
             keep.append(out_l)
@@ -196,6 +230,7 @@ class FusedPointnet2MSG:
             unknown, known = l_xyz[i], l_xyz[i + 1]
             d2, nn_idx = _ext.three_nn(unknown, known)
             nn_w = three_nn_weights(d2)
+            self._m("three_nn")
             known_feat = l_feat[i + 1]
             if known_feat.dim() == 2:
                 known_feat = known_feat.view(b, known.size(1), -1)
@@ -207,10 +242,13 @@ class FusedPointnet2MSG:
                 h = mlp_dense(h, lyr, round_out=not last, a_tf32=True)
             l_feat[i] = h.view(b, unknown.size(1), -1)
             feats[i] = (h.data_ptr(), h.size(-1), h.size(-1))
+            self._m("mlp")
         out_pm = l_feat[0]
         n_out = self.fp[0][-1].n
         if out_pm.size(-1) != n_out:
             out_pm = out_pm[..., :n_out].contiguous()
-        return _ext.transpose_nc_to_cn(out_pm)
+        out = _ext.transpose_nc_to_cn(out_pm)
+        self._m("glue")
+        return out
 
     __call__ = forward

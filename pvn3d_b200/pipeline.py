@@ -25,7 +25,7 @@ class FramePipeline:
     def __init__(self, shape: str, batch: int, n_points: int = fixtures.N_SAMPLE_POINTS, device="cuda",
                  lm_obj_id: int = 1, early_exit: bool = False, model: Optional[torch.nn.Module] = None,
                  allow_tf32: bool = True, engine: str = "fused", ms_mode: Optional[str] = None,
-                 overlap: bool = True):
+                 overlap: bool = True, bandwidth: float = 0.08):
         self.dev = torch.device(device)
         self.shape, self.b, self.n, self.k = shape, int(batch), int(n_points), fixtures.N_KEYPOINTS
         self.model = (model if model is not None else seeded_pointnet2msg(0, 1)).to(self.dev).eval()
@@ -38,12 +38,12 @@ class FramePipeline:
             self.n_cls = 2
             mesh = fixtures.mesh_kps_table_lm(lm_obj_id)
             self.solver = FramePoseSolver(self.b, self.n, self.k, 2, mesh, None, False, device=self.dev,
-                                          early_exit=early_exit, mode=ms_mode)
+                                          early_exit=early_exit, mode=ms_mode, bandwidth=bandwidth)
         elif shape == "ycb":
             self.n_cls = fixtures.YCB_N_CLASSES
             self.solver = FramePoseSolver(self.b, self.n, self.k, self.n_cls, fixtures.mesh_kps_table_ycb(),
                                           fixtures.radius_thresholds_ycb(), True, device=self.dev,
-                                          early_exit=early_exit, mode=ms_mode)
+                                          early_exit=early_exit, mode=ms_mode, bandwidth=bandwidth)
         else:
             raise ValueError(shape)
         self.allow_tf32 = allow_tf32
