@@ -35,6 +35,11 @@ def ms_flags(mode=None, early_exit=False, no_freeze=False) -> int:
 
 _ERR_NAMES = {-1: "invalid argument", -2: "unsupported size", -3: "CUDA error", -4: "workspace too small"}
 
+class MlpLayer(ctypes.Structure):
+    """pvn3d_mlp_layer_t (include/pvn3d_b200.h)"""
+    _fields_ = [("w", c_void_p), ("bias", c_void_p), ("k_pad", c_int), ("n_pad", c_int)]
+
+
 # name -> (restype, argtypes); mirrors include/pvn3d_b200.h one to one
 _P = c_void_p
 _SIGNATURES = {
@@ -60,6 +65,11 @@ _SIGNATURES = {
     "pvn3d_mlp_dense": (c_int, [_P, c_int, c_int, ctypes.c_longlong, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]),
     "pvn3d_mlp_sa_first": (c_int, [_P, _P, _P, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]),
     "pvn3d_mlp_fp_first": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, _P, c_int, c_int, _P]),
+    "pvn3d_mlp_chain_workspace_bytes": (c_size_t, [_P, c_int]),
+    "pvn3d_mlp_sa_chain": (c_int, [_P, _P, _P, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int,
+                                   _P, c_size_t, _P]),
+    "pvn3d_mlp_fp_chain": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int,
+                                   _P, c_size_t, _P]),
     "pvn3d_three_nn_weights": (c_int, [_P, ctypes.c_longlong, _P, _P]),
     "pvn3d_meanshift_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "pvn3d_meanshift_fit_batch": (c_int, [_P, _P, _P, c_int, c_int, c_double, c_int, c_uint, _P, _P, _P, _P, _P, c_size_t, _P]),

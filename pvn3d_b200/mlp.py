@@ -17,6 +17,8 @@ cuDNN / cuBLAS / ATen kernel runs in this path.
 """
 from __future__ import annotations
 
+import ctypes
+import os
 from typing import Dict, List, Tuple
 
 import torch
@@ -117,6 +119,56 @@ def mlp_fp_first(known_feat_pm, nn_idx, nn_w, skip_ptr, lds, c1, layer: PackedLa
     return out
 
 
+class LayerChain:
+    """the layers of one SharedMLP as the pvn3d_mlp_layer_t array pvn3d_mlp_{sa,fp}_chain take, plus the
+    scratch the chained kernel needs (inter-layer tiles of the CTAs, L2-resident)"""
+
+    def __init__(self, layers: List[PackedLayer]):
+        self.layers = layers
+        self.arr = (_lib.MlpLayer * len(layers))()
+        for i, pl in enumerate(layers):
+            self.arr[i].w, self.arr[i].bias = pl.w.data_ptr(), pl.bias.data_ptr()
+            self.arr[i].k_pad, self.arr[i].n_pad = pl.k_pad, pl.n_pad
+        self.n = len(layers)
+        self.ws_bytes = int(_lib.load().pvn3d_mlp_chain_workspace_bytes(ctypes.addressof(self.arr), self.n))
+        self.ws = torch.empty((self.ws_bytes + 16,), dtype=torch.uint8, device=layers[0].w.device)
+        self.ws_ptr = (self.ws.data_ptr() + 15) // 16 * 16
+
+    @property
+    def ptr(self) -> int:
+        return ctypes.addressof(self.arr)
+
+
+def mlp_sa_chain(xyz, new_xyz, feat_pm, ldf, c_feat, idx, chain: LayerChain, pool=0, out=None, col0=0):
+    """a whole SA-scale SharedMLP (QueryAndGroup producer -> layers -> max-pool) in one launch"""
+    lib = _lib.load()
+    b, n = xyz.shape[0], xyz.shape[1]
+    m, ns = idx.shape[1], idx.shape[2]
+    rows = b * m * ns
+    if out is None:
+        out = torch.empty((rows // pool if pool else rows, chain.layers[-1].n_pad), dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        rc = lib.pvn3d_mlp_sa_chain(ptr(xyz), ptr(new_xyz), feat_pm, ldf, c_feat, ptr(idx), b, n, m, ns, chain.ptr, chain.n,
+                                    pool, ptr(out), out.size(-1), col0, chain.ws_ptr, chain.ws_bytes, _stream(xyz.device))
+    check(rc, "pvn3d_mlp_sa_chain")
+    return out
+
+
+def mlp_fp_chain(known_feat_pm, nn_idx, nn_w, skip_ptr, lds, c1, chain: LayerChain, out=None):
+    """a whole FP-module SharedMLP (three_interpolate + concat producer -> layers) in one launch"""
+    lib = _lib.load()
+    b, m_known, c2 = known_feat_pm.shape
+    n_unknown = nn_idx.shape[1]
+    if out is None:
+        out = torch.empty((b * n_unknown, chain.layers[-1].n_pad), dtype=torch.float32, device=known_feat_pm.device)
+    with torch.cuda.device(known_feat_pm.device):
+        rc = lib.pvn3d_mlp_fp_chain(ptr(known_feat_pm), c2, ptr(nn_idx), ptr(nn_w), skip_ptr, lds, c1, b, n_unknown, m_known,
+                                    chain.ptr, chain.n, ptr(out), out.size(-1), 0, chain.ws_ptr, chain.ws_bytes,
+                                    _stream(known_feat_pm.device))
+    check(rc, "pvn3d_mlp_fp_chain")
+    return out
+
+
 def three_nn_weights(dist2: torch.Tensor) -> torch.Tensor:
     lib = _lib.load()
     w = torch.empty_like(dist2)
@@ -130,8 +182,13 @@ def three_nn_weights(dist2: torch.Tensor) -> torch.Tensor:
 class FusedPointnet2MSG:
     """Inference engine for Pointnet2MSG on libpvn3d_b200 only (see module docstring)."""
 
-    def __init__(self, model: torch.nn.Module, device="cuda"):
+    def __init__(self, model: torch.nn.Module, device="cuda", chain: bool | None = None):
         self.dev = torch.device(device)
+        #: chain=True: one launch per SharedMLP (inter-layer tiles stay in L2); False: one launch per layer.
+        #: Same bits either way (tests/test_mlp_gpu.py); PVN3D_MLP_CHAIN=0 selects the per-layer launches.
+        if chain is None:
+            chain = os.environ.get("PVN3D_MLP_CHAIN", "1") != "0"
+        self.chain = bool(chain)
         model = model.to(self.dev).eval()
         self.sa: List[List[List[PackedLayer]]] = []
         self.sa_out: List[int] = []
@@ -160,6 +217,8 @@ class FusedPointnet2MSG:
                 prev_pad = pl.n_pad
                 layers.append(pl)
             self.fp.append(layers)
+        self.sa_chain = [[LayerChain(layers) for layers in scales] for scales in self.sa] if self.chain else None
+        self.fp_chain = [LayerChain(layers) for layers in self.fp] if self.chain else None
         self._marks = None
 
     def _m(self, family: str) -> None:
@@ -213,7 +272,12 @@ class FusedPointnet2MSG:
             self._m("glue")
             idxs = _ext.ball_query2(new_xyz, x, radii, nsamples)    # one pass over the cloud for both radii
             self._m("ball")
-            for (idx, ns, layers) in zip(idxs, nsamples, self.sa[li]):
+            for si, (idx, ns, layers) in enumerate(zip(idxs, nsamples, self.sa[li])):
+                if self.chain:
+                    mlp_sa_chain(x, new_xyz, fptr, ldf, c_feat, idx, self.sa_chain[li][si], pool=ns,
+                                 out=out_l.view(b * npoint, -1), col0=col)
+                    col += layers[-1].n
+                    continue
                 # intermediates are stored TF32-rounded (what the next layer's operand is anyway)
                 h = mlp_sa_first(x, new_xyz, fptr, ldf, c_feat, idx, layers[0], round_out=True)
                 for mid in layers[1:-1]:
@@ -236,10 +300,13 @@ class FusedPointnet2MSG:
                 known_feat = known_feat.view(b, known.size(1), -1)
             sptr, lds, c1 = feats[i]
             layers = self.fp[i]
-            h = mlp_fp_first(known_feat, nn_idx, nn_w, sptr, lds, c1, layers[0], round_out=True)
-            for li2, lyr in enumerate(layers[1:]):
-                last = li2 == len(layers) - 2        # level tables stay full fp32
-                h = mlp_dense(h, lyr, round_out=not last, a_tf32=True)
+            if self.chain:
+                h = mlp_fp_chain(known_feat, nn_idx, nn_w, sptr, lds, c1, self.fp_chain[i])
+            else:
+                h = mlp_fp_first(known_feat, nn_idx, nn_w, sptr, lds, c1, layers[0], round_out=True)
+                for li2, lyr in enumerate(layers[1:]):
+                    last = li2 == len(layers) - 2        # level tables stay full fp32
+                    h = mlp_dense(h, lyr, round_out=not last, a_tf32=True)
             l_feat[i] = h.view(b, unknown.size(1), -1)
             feats[i] = (h.data_ptr(), h.size(-1), h.size(-1))
             self._m("mlp")
