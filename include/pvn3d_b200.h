@@ -280,6 +280,26 @@ int pvn3d_frame_poses_batch(const float *pcld, const int *mask, const float *ctr
                             uint8_t *present, float *cls_kps, int *new_mask, void *workspace,
                             size_t workspace_bytes, pvn3d_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Callers either side of the path
+ * ---------------------------------------------------------------------------------------- */
+
+/* labels[p] = argmax_c logits[p, c] -- `_, classes_rgbd = torch.max(pred_rgbd_seg, -1)` (demo.py:108):
+ * first maximal index; the int32 output is the `mask` pvn3d_frame_poses_batch takes.
+ *   logits [rows, n_cls] f32 -> labels [rows] i32 */
+int pvn3d_seg_argmax(const float *logits, long long rows, int n_cls, int *labels, pvn3d_stream_t stream);
+
+/* ADD and ADD-S of n_poses (predicted, ground-truth) pose pairs over one mesh: Basic_Utils.cal_add_cuda /
+ * cal_adds_cuda (basic_utils.py:617-635).
+ *   pred_rt, gt_rt [n_poses,3,4] f32, p3ds [n_points,3] f32 (object frame)
+ *   add[i]  = mean_k | (R_p x_k + t_p) - (R_g x_k + t_g) |
+ *   adds[i] = mean_k min_j | (R_p x_j + t_p) - (R_g x_k + t_g) |          (either output may be NULL)
+ * fp32 with fused multiply-adds; the per-block sums are combined in a fixed order (reproducible). */
+size_t pvn3d_pose_add_adds_workspace_bytes(int n_poses, int n_points);
+int pvn3d_pose_add_adds(const float *pred_rt, const float *gt_rt, int n_poses, const float *p3ds,
+                        int n_points, float *add, float *adds, void *workspace, size_t workspace_bytes,
+                        pvn3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

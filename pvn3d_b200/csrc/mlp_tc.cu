@@ -28,6 +28,8 @@
 //
 // TF32: operands are rounded to nearest (cvt.rna.tf32.f32) when staged, accumulation is fp32 -- the
 // precision class of the reference's default cuDNN convolutions (torch.backends.cudnn.allow_tf32).
+#include <cuda.h>  // CUtensorMap + the cuTensorMapEncodeTiled prototype (entry point fetched through the runtime)
+
 #include "common.cuh"
 
 namespace pvn3d {
@@ -111,6 +113,20 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+// register transaction bytes on an mbarrier WITHOUT arriving (the thread arrives later like every producer)
+__device__ __forceinline__ void mbar_expect_tx_only(uint64_t *bar, unsigned bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+// one 2-D tile global -> shared through a tensor map (TMA), completion counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap *map, int x, int y,
+                                            uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+          "r"(dst_smem),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                           uint32_t idesc, uint32_t accumulate) {
@@ -722,6 +738,10 @@ struct ChainLayer {
   int k_pad, n_pad, bn, n_blocks;
 };
 struct MlpChainArgs {
+  // weight matrices as TMA tensor maps: [n_pad][k_pad] fp32, box = 32 columns (128 B) x bn rows,
+  // SWIZZLE_128B -- one cp.async.bulk.tensor.2d per K chunk lands the B operand in the UMMA layout
+  alignas(64) CUtensorMap tmap[3];
+  int use_tma;
   MlpArgs base;        // producer of layer 0 + final epilogue (rows, out, ldo, col0, pool)
   ChainLayer layer[3];
   int n_layers;
@@ -864,9 +884,18 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_kernel(const __grid_
               mbar_wait(&ctl.empty[s], static_cast<unsigned>(((it / S) & 1) ^ 1));
               const uint32_t sa = ring + static_cast<uint32_t>(s) * stage_bytes;
               const uint32_t sb = sa + a_bytes;
-              for (int i = pt; i < bn * 8; i += 128) {
-                const int n = i >> 3, cc = i & 7;
-                cp_async16(sb + sw128_off(n, cc), L.w + static_cast<size_t>(n0 + n) * L.k_pad + kc * 32 + cc * 4);
+              if (c.use_tma) {
+                // B operand by the TMA engine: rows n0..n0+L.bn of W, columns kc*32..+32, swizzled on the fly;
+                // completes on the stage's `full` barrier (transaction bytes registered first)
+                if (pt == 0) {
+                  mbar_expect_tx_only(&ctl.full[s], static_cast<unsigned>(L.bn) * 128u);
+                  tma_load_2d(sb, &c.tmap[l], kc * 32, n0, &ctl.full[s]);
+                }
+              } else {
+                for (int i = pt; i < bn * 8; i += 128) {
+                  const int n = i >> 3, cc = i & 7;
+                  cp_async16(sb + sw128_off(n, cc), L.w + static_cast<size_t>(n0 + n) * L.k_pad + kc * 32 + cc * 4);
+                }
               }
               if (l > 0) {
                 const int k = kc * 32 + 4 * sub;
@@ -1083,6 +1112,47 @@ int chain_plan(MlpChainArgs &c, const pvn3d_mlp_layer_t *layers, int n_layers) {
   return off;
 }
 
+// cuTensorMapEncodeTiled lives in libcuda; the library links only the runtime, so the entry point is
+// fetched once through cudaGetDriverEntryPoint
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+    tried = true;
+  }
+  return fn;
+}
+
+// tensor maps of the chain's weight matrices; false -> the kernel falls back to per-thread cp.async
+bool chain_tensor_maps(MlpChainArgs &c) {
+  const char *env = getenv("PVN3D_MLP_TMA");
+  if (env && env[0] == '0') return false;
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  for (int l = 0; l < c.n_layers; ++l) {
+    const ChainLayer &L = c.layer[l];
+    if (reinterpret_cast<uintptr_t>(L.w) & 15u) return false;
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(L.k_pad), static_cast<cuuint64_t>(L.n_pad)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(L.k_pad) * sizeof(float)};
+    const cuuint32_t box[2] = {32u, static_cast<cuuint32_t>(L.bn)};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = enc(&c.tmap[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(L.w), dims,
+                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+  }
+  return true;
+}
+
 bool chain_layers_ok(const pvn3d_mlp_layer_t *layers, int n_layers, int k_first_min) {
   if (!layers || n_layers < 1 || n_layers > 3) return false;
   for (int l = 0; l < n_layers; ++l) {
@@ -1117,6 +1187,7 @@ int launch_chain(MlpChainArgs &c, void *workspace, size_t workspace_bytes, cudaS
   if (c.n_layers > 1 && (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15u)))
     return PVN3D_ERR_WORKSPACE;
   c.scratch = static_cast<float *>(workspace);
+  c.use_tma = chain_tensor_maps(c) ? 1 : 0;
   kern<<<grid, kMlpThreads, smem, st>>>(c);
   return check_launch("mlp_chain_kernel");
 }

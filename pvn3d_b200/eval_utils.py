@@ -154,3 +154,55 @@ def best_fit_transform(A, B) -> np.ndarray:
                                                 torch.cuda.current_stream(a.device).cuda_stream)
     check(rc, "pvn3d_best_fit_transform_batch")
     return rt[0].double().cpu().numpy()
+
+
+# --------------------------------------------------------------------------------------------------
+# callers either side of the path: segmentation argmax, ADD / ADD-S
+# --------------------------------------------------------------------------------------------------
+def seg_argmax(logits: torch.Tensor) -> torch.Tensor:
+    """`_, classes_rgbd = torch.max(pred_rgbd_seg, -1)` (demo.py:108) as one kernel: logits [..., n_cls] f32
+    -> int32 class ids [...] -- the `mask` FramePoseSolver.solve takes (first maximal index)."""
+    if not logits.is_cuda:
+        raise RuntimeError("seg_argmax (pvn3d_b200): CUDA tensors only -- no CPU fallback")
+    lib = _lib.load()
+    x = logits.contiguous().float()
+    n_cls = x.size(-1)
+    out = torch.empty(x.shape[:-1], dtype=torch.int32, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.pvn3d_seg_argmax(ptr(x), x.numel() // n_cls, n_cls, ptr(out), torch.cuda.current_stream(x.device).cuda_stream)
+    check(rc, "pvn3d_seg_argmax")
+    return out
+
+
+def pose_add_adds(pred_RT: torch.Tensor, gt_RT: torch.Tensor, p3ds: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """ADD and ADD-S of F pose pairs over one mesh in two launches: pred_RT, gt_RT [F,3,4] (or [3,4]),
+    p3ds [P,3] -> (add [F], adds [F]).  basic_utils.py:617-635."""
+    if not p3ds.is_cuda:
+        raise RuntimeError("pose_add_adds (pvn3d_b200): CUDA tensors only -- no CPU fallback")
+    lib = _lib.load()
+    dev = p3ds.device
+    pr = pred_RT.reshape(-1, 3, 4).to(dev, torch.float32).contiguous()
+    gt = gt_RT.reshape(-1, 3, 4).to(dev, torch.float32).contiguous()
+    assert pr.shape == gt.shape
+    pts = p3ds.to(torch.float32).contiguous()
+    f, p = pr.size(0), pts.size(0)
+    add = torch.empty((f,), dtype=torch.float32, device=dev)
+    adds = torch.empty((f,), dtype=torch.float32, device=dev)
+    ws_bytes = int(lib.pvn3d_pose_add_adds_workspace_bytes(f, p))
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.pvn3d_pose_add_adds(ptr(pr), ptr(gt), f, ptr(pts), p, ptr(add), ptr(adds), ptr(ws), ws_bytes,
+                                     torch.cuda.current_stream(dev).cuda_stream)
+    check(rc, "pvn3d_pose_add_adds")
+    ws.record_stream(torch.cuda.current_stream(dev))
+    return add, adds
+
+
+def cal_add_cuda(pred_RT, gt_RT, p3ds) -> torch.Tensor:
+    """Basic_Utils.cal_add_cuda (basic_utils.py:617-623): 0-dim tensor"""
+    return pose_add_adds(pred_RT, gt_RT, p3ds)[0][0]
+
+
+def cal_adds_cuda(pred_RT, gt_RT, p3ds) -> torch.Tensor:
+    """Basic_Utils.cal_adds_cuda (basic_utils.py:625-635): 0-dim tensor"""
+    return pose_add_adds(pred_RT, gt_RT, p3ds)[1][0]

@@ -27,7 +27,7 @@ REF = "/root/reference/pvn3d"
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 from pvn3d_b200 import compat, fixtures, synth, testing  # noqa: E402
-from oracle import ext_cpu, frame_poses_oracle, meanshift_oracle  # noqa: E402
+from oracle import ext_cpu, frame_poses_oracle, meanshift_oracle, metrics_oracle  # noqa: E402
 
 compat.install_import_shims()
 sys.modules["lib.pointnet2_utils._ext"] = ext_cpu
@@ -176,9 +176,43 @@ def golden_pn2msg():
                         feat_abs_mean=np.float64(y.double().abs().mean()))
 
 
+def golden_metrics():
+    """Basic_Utils.cal_add_cuda / cal_adds_cuda (basic_utils.py:617-635) on CPU float32 tensors: a random
+    mesh of 1500 points, pose pairs from identical to 5 cm / 20 degrees apart, and a symmetric object
+    (ADD large, ADD-S ~ 0)."""
+    bs = ref_eval.bs_utils
+    rng = np.random.default_rng(41)
+    mesh = rng.uniform(-0.08, 0.08, size=(1500, 3)).astype(np.float32)
+    sym = np.concatenate([mesh[:750], -mesh[:750]], 0)            # point-symmetric: R = -I maps it onto itself
+    pred, gt, which, add, adds = [], [], [], [], []
+    for i in range(6):
+        Rg = synth._haar_rotation(rng)
+        tg = rng.uniform([-0.2, -0.2, 0.6], [0.2, 0.2, 1.0])
+        ang = [0.0, 0.01, 0.05, 0.35, 0.0, 0.1][i]
+        ax = rng.normal(size=3); ax /= np.linalg.norm(ax)
+        K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+        dR = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K
+        Rp = dR @ Rg
+        tp = tg + rng.normal(0, [0.0, 0.002, 0.01, 0.05, 0.0, 0.003][i], 3)
+        use_sym = i == 4
+        if use_sym:
+            Rp = -Rg                                                # improper but isometric: exercises ADD >> ADD-S
+        m = sym if use_sym else mesh
+        P = np.concatenate([Rp, tp[:, None]], 1).astype(np.float32)
+        G = np.concatenate([Rg, tg[:, None]], 1).astype(np.float32)
+        a = bs.cal_add_cuda(torch.from_numpy(P), torch.from_numpy(G), torch.from_numpy(m))
+        s = bs.cal_adds_cuda(torch.from_numpy(P), torch.from_numpy(G), torch.from_numpy(m))
+        assert torch.equal(a, metrics_oracle.cal_add(torch.from_numpy(P), torch.from_numpy(G), torch.from_numpy(m)))
+        assert torch.equal(s, metrics_oracle.cal_adds(torch.from_numpy(P), torch.from_numpy(G), torch.from_numpy(m)))
+        pred.append(P); gt.append(G); which.append(int(use_sym)); add.append(float(a)); adds.append(float(s))
+        print(f"  metrics case {i}: ADD {float(a):.6f}  ADD-S {float(s):.6f}")
+    np.savez_compressed(os.path.join(OUT, "metrics.npz"), mesh=mesh, sym=sym, pred=np.stack(pred), gt=np.stack(gt),
+                        which=np.array(which, np.int32), add=np.array(add, np.float32), adds=np.array(adds, np.float32))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(os.cpu_count())
-    which = sys.argv[1:] or ["ms", "bft", "poses", "pn2msg"]
+    which = sys.argv[1:] or ["ms", "bft", "poses", "pn2msg", "metrics"]
     if "ms" in which:
         golden_meanshift()
     if "bft" in which:
@@ -187,4 +221,6 @@ if __name__ == "__main__":
         golden_poses()
     if "pn2msg" in which:
         golden_pn2msg()
+    if "metrics" in which:
+        golden_metrics()
     print("done")

@@ -211,3 +211,21 @@ def test_cell_list_ball_query_prototype_matches_oracle():
         for g, r, ns in zip(got, radii, nss):
             want = pn2.ball_query(new[None], xyz[None], float(np.float32(r)), ns)[0]
             assert np.array_equal(g, want), (n, r, ns)
+
+
+def test_metrics_oracle_matches_reference_golden():
+    """ADD / ADD-S restatement (oracle/metrics_oracle.py) against values recorded from the reference's
+    Basic_Utils.cal_add_cuda / cal_adds_cuda (tests/golden/metrics.npz)"""
+    import os
+
+    import numpy as np
+    import torch
+
+    from oracle import metrics_oracle
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "metrics.npz"))
+    for i in range(len(z["which"])):
+        mesh = torch.from_numpy(z["sym"] if z["which"][i] else z["mesh"])
+        a = metrics_oracle.cal_add(torch.from_numpy(z["pred"][i]), torch.from_numpy(z["gt"][i]), mesh)
+        s = metrics_oracle.cal_adds(torch.from_numpy(z["pred"][i]), torch.from_numpy(z["gt"][i]), mesh)
+        assert np.float32(a) == z["add"][i] and np.float32(s) == z["adds"][i]
