@@ -252,11 +252,14 @@ def workload_name(cfg):
 class Runner:
     """one configuration: frames, pipeline, rotating device / pinned host batches, timed loops"""
 
-    def __init__(self, torch, cfg, dev, rank, world, ms_mode, overlap=True, engine="fused", bandwidth=0.08, n_rot=4):
+    def __init__(self, torch, cfg, dev, rank, world, ms_mode, overlap=True, engine="fused", bandwidth=0.08, n_rot=4,
+                 lookahead=True):
         from pvn3d_b200 import synth
         from pvn3d_b200.pipeline import FramePipeline
 
         self.torch, self.cfg, self.dev, self.rank, self.world = torch, cfg, dev, rank, world
+        #: the loop names the next batch, so its coordinate-only work (FPS, ball query, 3-NN) runs under this batch's MLPs
+        self.lookahead = bool(lookahead and overlap)
         B = self.B = cfg["batch"]
         kw = dict(lm_obj_id=1) if cfg["shape"] == "linemod" else {}
         if cfg.get("n_inst"):
@@ -264,7 +267,9 @@ class Runner:
         self.frames = synth.make_batch(cfg["shape"], B, n_points=cfg["n_points"], config_id=cfg["config_id"],
                                        first_frame=rank * B, **kw)
         self.pipe = FramePipeline(cfg["shape"], B, n_points=cfg["n_points"], device=dev, lm_obj_id=1, ms_mode=ms_mode,
-                                  engine=engine, overlap=overlap, bandwidth=bandwidth)
+                                  engine=engine, overlap=overlap, bandwidth=bandwidth,
+                                  pose_stream=os.environ.get("PVN3D_POSE_STREAM", "1") != "0",
+                                  fps_chunk=int(os.environ.get("PVN3D_FPS_CHUNK", "16")))
         host = synth.stack(self.frames)
         self.n_rot = n_rot
         self.host_rot = [FramePipeline.pin_batch({k: np.roll(v, (B // n_rot) * r, axis=0) for k, v in host.items()})
@@ -276,12 +281,13 @@ class Runner:
 
     def step_device(self, i):
         d = self.dev_rot[i % self.n_rot]
-        poses, _ = self.pipe.run_device(d["cld_rgb_nrm"], d["pcld"], d["labels"], d["ctr_of"], d["kp_of"])
+        nxt = self.dev_rot[(i + 1) % self.n_rot]["cld_rgb_nrm"] if self.lookahead else None
+        poses, _ = self.pipe.run_device(d["cld_rgb_nrm"], d["pcld"], d["labels"], d["ctr_of"], d["kp_of"], next_cloud=nxt)
         if self.world > 1:   # the single collective of the path: ~1.5 kB per frame
             self.torch.distributed.all_gather_into_tensor(self.gather_buf, poses.reshape(-1))
 
     def step_host(self, i):
-        self.pipe.run_host(self.host_rot[i % self.n_rot])
+        self.pipe.run_host(self.host_rot[i % self.n_rot], self.host_rot[(i + 1) % self.n_rot] if self.lookahead else None)
         if self.world > 1:
             self.torch.distributed.all_gather_into_tensor(self.gather_buf, self.pipe.solver.poses.reshape(-1))
 
@@ -482,7 +488,8 @@ def b200_arm(args, json_out):
     peak, peak_kind = load_peaks()
     overlap = not args.no_overlap
 
-    run = Runner(torch, cfg, dev, rank, world, args.ms_mode, overlap=overlap, engine=args.engine)
+    la = not args.no_lookahead
+    run = Runner(torch, cfg, dev, rank, world, args.ms_mode, overlap=overlap, engine=args.engine, lookahead=la)
     head = run.measure(args.steps, args.warmup, lib)
     B = run.B
     line = None
@@ -500,7 +507,9 @@ def b200_arm(args, json_out):
                                          "early_exit": "early_exit: all seeds, reference stop rule or stationary returned seed",
                                          "strict": "strict: all seeds, the reference's global stop rule (reference iteration counts)",
                                          "no_freeze": "no_freeze: literal reference schedule"}[args.ms_mode],
-                           "overlap": "hot path B on its own stream under hot path A" if overlap else "single stream"},
+                           "overlap": ("hot path B on its own stream under hot path A" if overlap else "single stream")
+                                      + ("; look-ahead: geometry (FPS / ball query / 3-NN) of batch i+1 on a third stream under "
+                                         "the shared MLPs of batch i" if (la and overlap) else "")},
                 "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": head["clocks"],
                 "frames_per_s_hbm_frac": {"value": head["value"] / world / (peak * 1e9 / FRAME_HBM_BYTES),
                                           "per_gpu_roofline_frames_per_s": peak * 1e9 / FRAME_HBM_BYTES,
@@ -587,7 +596,8 @@ def b200_arm(args, json_out):
         subs = {}
         del run
         torch.cuda.empty_cache()
-        r2 = Runner(torch, CONFIGS["ycb"], dev, rank, world, args.ms_mode, overlap=overlap, engine=args.engine, n_rot=4)
+        r2 = Runner(torch, CONFIGS["ycb"], dev, rank, world, args.ms_mode, overlap=overlap, engine=args.engine, n_rot=4,
+                    lookahead=la)
         m = r2.measure(max(5, args.steps // 2), 3, lib)
         key = f"ycb_b{CONFIGS['ycb']['batch']}" if world == 1 else f"ycb_b{CONFIGS['ycb']['batch'] * world}_sharded_x{world}"
         if rank == 0:
@@ -600,7 +610,8 @@ def b200_arm(args, json_out):
             subs[key] = m
         del r2
         torch.cuda.empty_cache()
-        r3 = Runner(torch, CONFIGS["stress"], dev, rank, world, args.ms_mode, overlap=overlap, engine=args.engine, n_rot=2)
+        r3 = Runner(torch, CONFIGS["stress"], dev, rank, world, args.ms_mode, overlap=overlap, engine=args.engine, n_rot=2,
+                    lookahead=la)
         m = r3.measure(max(3, args.steps // 4), 3, lib, e2e=True)
         if rank == 0:
             m["workload"] = workload_name(CONFIGS["stress"]) + (f", {world} GPUs" if world > 1 else "")
@@ -653,6 +664,8 @@ def main():
     ap.add_argument("--config", default="linemod", choices=["linemod", "ycb"])
     ap.add_argument("--ms-mode", default="certified", choices=["certified", "early_exit", "strict", "no_freeze"])
     ap.add_argument("--no-overlap", action="store_true", help="run hot path B after hot path A on one stream")
+    ap.add_argument("--no-lookahead", action="store_true",
+                    help="do not compute the next batch's geometry plan under this batch's MLPs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="headline + stage split only (development runs, ncu)")
     ap.add_argument("--engine", default="fused", choices=["fused", "modules"],

@@ -63,6 +63,9 @@ int pvn3d_furthest_point_sampling(const float *xyz, int b, int n, int m, int *id
 /* gather_points(points[B,C,N], idx[B,M]) -> out[B,C,M]        (sampling.h:4, sampling_gpu.cu:8-30) */
 int pvn3d_gather_points(const float *points, const int *idx, int b, int c, int n, int m,
                         float *out, pvn3d_stream_t stream);
+/* new_xyz[B,M,3] = xyz[B, idx[B,M], :]: the point-major form of the reference's
+ * gather_operation(xyz.transpose(1,2), idx).transpose(1,2) (pointnet2_modules.py:47-53), no transposes */
+int pvn3d_gather_xyz(const float *xyz, const int *idx, int b, int n, int m, float *out, pvn3d_stream_t stream);
 /* gather_points_grad(grad_out[B,C,M], idx[B,M], N) -> grad_points[B,C,N]  (sampling_gpu.cu:34-57);
  * grad_points is zero-filled by the callee, then scatter-added. */
 int pvn3d_gather_points_grad(const float *grad_out, const int *idx, int b, int c, int n, int m,
@@ -157,6 +160,9 @@ int pvn3d_three_nn_interpolate(const float *unknown, const float *known, const f
 #define PVN3D_MLP_RELU 1
 #define PVN3D_MLP_ROUND_OUT 2
 #define PVN3D_MLP_A_TF32 4
+/* leave n SMs (0..255) to kernels running concurrently on other streams: the persistent grid is
+ * sm_count - n CTAs instead of one per SM (a persistent CTA that cannot be placed stalls its kernel) */
+#define PVN3D_MLP_RESERVE_SMS(n) (((n) & 0xff) << 8)
 
 /* A = point-major activations a[rows, lda]; columns >= a_cols read as zero. */
 int pvn3d_mlp_dense(const float *a, int lda, int a_cols, long long rows, const float *w,
@@ -182,6 +188,7 @@ int pvn3d_mlp_fp_first(const float *known_feat_pm, int c2, const int *nn_idx, co
  *   pvn3d_mlp_sa_chain: SA scale = QueryAndGroup producer (as pvn3d_mlp_sa_first) -> layers -> max-pool over
  *                       nsample when pool == ns (pointnet2_modules.py:58-69), else the point-major rows
  *   pvn3d_mlp_fp_chain: FP module = three_interpolate + concat producer (as pvn3d_mlp_fp_first) -> layers
+ *   flags: only PVN3D_MLP_RESERVE_SMS(n) (every layer applies ReLU)
  *   workspace: pvn3d_mlp_chain_workspace_bytes(layers, n_layers) bytes, 16-byte aligned, private to the
  *              launch until it completes.
  * Results are identical to running the per-layer entry points above with PVN3D_MLP_ROUND_OUT between the
@@ -194,12 +201,12 @@ typedef struct {
 size_t pvn3d_mlp_chain_workspace_bytes(const pvn3d_mlp_layer_t *layers, int n_layers);
 int pvn3d_mlp_sa_chain(const float *xyz, const float *new_xyz, const float *feat_pm, int ldf, int c_feat,
                        const int *idx, int b, int n, int m, int ns, const pvn3d_mlp_layer_t *layers,
-                       int n_layers, int pool, float *out, int ldo, int col0, void *workspace,
+                       int n_layers, int flags, int pool, float *out, int ldo, int col0, void *workspace,
                        size_t workspace_bytes, pvn3d_stream_t stream);
 int pvn3d_mlp_fp_chain(const float *known_feat_pm, int c2, const int *nn_idx, const float *nn_w,
                        const float *skip_pm, int lds, int c1, int b, int n_unknown, int m_known,
-                       const pvn3d_mlp_layer_t *layers, int n_layers, float *out, int ldo, int col0,
-                       void *workspace, size_t workspace_bytes, pvn3d_stream_t stream);
+                       const pvn3d_mlp_layer_t *layers, int n_layers, int flags, float *out, int ldo,
+                       int col0, void *workspace, size_t workspace_bytes, pvn3d_stream_t stream);
 /* weight[p,0:3] = (1/(sqrt(dist2)+1e-8)) / sum  (pointnet2_modules.py:184-186), fp32 IEEE ops */
 int pvn3d_three_nn_weights(const float *dist2, long long rows, float *weight, pvn3d_stream_t stream);
 

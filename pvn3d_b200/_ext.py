@@ -82,6 +82,18 @@ def gather_points(points: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def gather_xyz(xyz: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """xyz [B,N,3] f32, idx [B,M] i32 -> new_xyz [B,M,3] (point-major gather_operation, pointnet2_modules.py:47-53)"""
+    _chk_contig(xyz, "xyz"); _chk_contig(idx, "idx")
+    _chk_float(xyz, "xyz"); _chk_int(idx, "idx")
+    _need_cuda(xyz)
+    b, n, _ = xyz.shape
+    m = idx.size(1)
+    out = torch.empty((b, m, 3), dtype=torch.float32, device=xyz.device)
+    _call("pvn3d_gather_xyz", xyz.device, ptr(xyz), ptr(idx), b, n, m, ptr(out))
+    return out
+
+
 def gather_points_grad(grad_out: torch.Tensor, idx: torch.Tensor, n: int) -> torch.Tensor:
     """sampling.cpp:40-63"""
     _chk_contig(grad_out, "grad_out")

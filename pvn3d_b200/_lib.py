@@ -50,6 +50,7 @@ _SIGNATURES = {
     "pvn3d_launch_count": (ctypes.c_ulonglong, []),
     "pvn3d_furthest_point_sampling": (c_int, [_P, c_int, c_int, c_int, _P, _P]),
     "pvn3d_gather_points": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
+    "pvn3d_gather_xyz": (c_int, [_P, _P, c_int, c_int, c_int, _P, _P]),
     "pvn3d_gather_points_grad": (c_int, [_P, _P, c_int, c_int, c_int, c_int, _P, _P]),
     "pvn3d_ball_query": (c_int, [_P, _P, c_int, c_int, c_int, c_float, c_int, _P, _P]),
     "pvn3d_group_points": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P]),
@@ -66,9 +67,9 @@ _SIGNATURES = {
     "pvn3d_mlp_sa_first": (c_int, [_P, _P, _P, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P]),
     "pvn3d_mlp_fp_first": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, _P, c_int, c_int, _P]),
     "pvn3d_mlp_chain_workspace_bytes": (c_size_t, [_P, c_int]),
-    "pvn3d_mlp_sa_chain": (c_int, [_P, _P, _P, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int,
-                                   _P, c_size_t, _P]),
-    "pvn3d_mlp_fp_chain": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, _P, c_int, c_int,
+    "pvn3d_mlp_sa_chain": (c_int, [_P, _P, _P, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, c_int, c_int, c_int, _P, c_int,
+                                   c_int, _P, c_size_t, _P]),
+    "pvn3d_mlp_fp_chain": (c_int, [_P, c_int, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, c_int, c_int, _P, c_int, c_int,
                                    _P, c_size_t, _P]),
     "pvn3d_three_nn_weights": (c_int, [_P, ctypes.c_longlong, _P, _P]),
     "pvn3d_seg_argmax": (c_int, [_P, ctypes.c_longlong, c_int, _P, _P]),

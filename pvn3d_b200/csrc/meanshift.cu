@@ -160,9 +160,14 @@ __global__ void __launch_bounds__(1024) ms_setup_kernel(MsArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// exact density pass: one thread per input point, all points of the fit swept from shared memory
+// exact density pass: one thread per input point, all points of the fit swept from shared memory.
+// The tile holds point PAIRS (x0,x1,y0,y1 | z0,z1) so that the distance of one seed to two points is
+// three FADD2 + FMUL2 + two FFMA2 on the packed fp32 pipe: per lane these are the same IEEE operations in
+// the same order as torch_sqnorm (fma(dz,dz, fma(dy,dy, dx*dx)) on p - me), so counts stay bit-exact, at
+// 6 instead of 9 issue slots per pair test.
 __global__ void __launch_bounds__(kMsThreads) ms_density_kernel(MsArgs a) {
-  __shared__ float4 s_pts[kMsDensTile];
+  __shared__ float4 s_xy[kMsDensTile / 2];   // (x0, x1, y0, y1)
+  __shared__ float2 s_z[kMsDensTile / 2];    // (z0, z1)
   __shared__ unsigned long long s_key[kMsWarps];
   const int tile = blockIdx.x;
   if (tile >= a.dens_prefix[a.n_fits]) return;
@@ -171,18 +176,32 @@ __global__ void __launch_bounds__(kMsThreads) ms_density_kernel(MsArgs a) {
   const int i = (tile - a.dens_prefix[f]) * kMsThreads + threadIdx.x;
   const bool live = i < cnt;
   const float4 me = a.pts[start + (live ? i : 0)];
+  const float2 nx = make_float2(-me.x, -me.x), ny = make_float2(-me.y, -me.y), nz = make_float2(-me.z, -me.z);
   const float t2 = a.t2;
+  const float inf = __int_as_float(0x7f800000);
   int count = 0;
   for (int base = 0; base < cnt; base += kMsDensTile) {
     const int n = min(kMsDensTile, cnt - base);
+    const int npairs = (n + 1) >> 1;
     __syncthreads();
-    for (int q = threadIdx.x; q < n; q += kMsThreads) s_pts[q] = a.pts[start + base + q];
+    for (int q = threadIdx.x; q < npairs; q += kMsThreads) {
+      const float4 p0 = a.pts[start + base + 2 * q];
+      // odd tail: a point at infinity is never an inlier (inf < t2 is false)
+      const float4 p1 = 2 * q + 1 < n ? a.pts[start + base + 2 * q + 1] : make_float4(inf, inf, inf, 0.f);
+      s_xy[q] = make_float4(p0.x, p1.x, p0.y, p1.y);
+      s_z[q] = make_float2(p0.z, p1.z);
+    }
     __syncthreads();
-#pragma unroll 8
-    for (int j = 0; j < n; ++j) {
-      const float4 p = s_pts[j];
+#pragma unroll 4
+    for (int j = 0; j < npairs; ++j) {
+      const float4 xy = s_xy[j];
+      const float2 z = s_z[j];
       // dis = torch.norm(Ar - Cr): diff = A_j - A_i   (meanshift_pytorch.py:46-48)
-      count += torch_sqnorm(p.x - me.x, p.y - me.y, p.z - me.z) < t2 ? 1 : 0;
+      const float2 dx = __fadd2_rn(make_float2(xy.x, xy.y), nx);
+      const float2 dy = __fadd2_rn(make_float2(xy.z, xy.w), ny);
+      const float2 dz = __fadd2_rn(z, nz);
+      const float2 d2 = __ffma2_rn(dz, dz, __ffma2_rn(dy, dy, __fmul2_rn(dx, dx)));
+      count += (d2.x < t2 ? 1 : 0) + (d2.y < t2 ? 1 : 0);
     }
   }
   if (live) a.dens_cnt[start + i] = count;
@@ -776,6 +795,108 @@ __global__ void __launch_bounds__(kMsThreads, 2) ms_witness_kernel(MsArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fallback of PVN3D_MS_CERTIFIED: the fits the witnesses could not close (typically clean vote sets whose
+// global stop rule fires within a few iterations) are iterated over ALL seeds by ONE CTA per fit, in lock
+// step like the reference loop, with the rule of PVN3D_MS_EARLY_EXIT: stop at the first iteration at which no
+// seed moves by >= bw*1e-3 (the reference's T), or at which the returned seed is stationary.  Seeds that
+// stopped moving (< 1e-6*bw) are skipped like in ms_iterate_kernel.
+// Unlike ms_iterate_kernel this is an ordinary launch: no grid barrier, no co-residency requirement -- a
+// cooperative grid of 3 CTAs on EVERY SM cannot start while the persistent MLP kernels of hot path A and the
+// sampling CTAs of the look-ahead stream hold SMs, and would serialise the streams of the frame pipeline.
+struct MsFbSmem {
+  float4 pts[kMsPtTile];
+  int violated[3];   // flag of iteration it lives in slot it % 3; slot (it+1) % 3 is cleared during iteration it
+                     // (last read at the end of iteration it-2, a barrier ago)
+  int star_still;
+  float4 star_pos;
+};
+
+__global__ void __launch_bounds__(kMsThreads, 3) ms_fallback_kernel(MsArgs a) {
+  extern __shared__ __align__(16) unsigned char ms_smem_raw[];
+  MsFbSmem &sm = *reinterpret_cast<MsFbSmem *>(ms_smem_raw);
+  const int f = blockIdx.x;
+  const int n_c = a.fit_count[f];
+  if (n_c <= 0 || a.done[f]) return;   // empty, or certified
+  const int start = a.fit_start[f], star = a.max_idx[f];
+  const int last_it = a.max_iter + 1;
+  const bool single = n_c <= kMsPtTile;
+  const int t = threadIdx.x;
+  const float k = a.kexp;
+  const float4 *cpts = a.cpts + start;
+  float4 *seeds = a.seeds + start;
+  constexpr int R = 2;
+  if (single) ms_stage_pairs(sm.pts, cpts, n_c);
+  if (t == 0) { sm.violated[0] = sm.violated[1] = sm.violated[2] = 0; sm.star_still = 0; sm.star_pos = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __syncthreads();
+  int T = last_it;
+  for (int it = 1; it <= last_it; ++it) {
+    if (t == 0) sm.violated[(it + 1) % 3] = 0;
+    for (int base = 0; base < n_c; base += kMsThreads * R) {
+      int idx[R];
+      float cx[R], cy[R], cz[R];
+      bool skip[R];
+      bool any = false;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        idx[r] = base + r * kMsThreads + t;
+        const bool valid = idx[r] < n_c;
+        const float4 c = seeds[valid ? idx[r] : 0];
+        cx[r] = c.x; cy[r] = c.y; cz[r] = c.z;
+        skip[r] = !valid || (it > 1 && c.w < a.eps_stat);   // .w = shift of the previous iteration
+        any |= !skip[r];
+      }
+      const bool warp_live = __any_sync(0xffffffffu, any);
+      MsSeedQ sq[R];
+      MsSeedS ss[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        sq[r] = ms_seed_q(k, cx[r], cy[r], cz[r]);
+        ss[r].sw = ss[r].sx = ss[r].sy = ss[r].sz = make_float2(0.f, 0.f);
+      }
+      if (single) {
+        if (warp_live) ms_sweep<R>(sm.pts, (n_c + 1) >> 1, sq, ss);
+      } else {
+        for (int pb = 0; pb < n_c; pb += kMsPtTile) {
+          const int n = min(kMsPtTile, n_c - pb);
+          __syncthreads();
+          ms_stage_pairs(sm.pts, cpts + pb, n);
+          __syncthreads();
+          if (warp_live) ms_sweep<R>(sm.pts, (n + 1) >> 1, sq, ss);
+        }
+      }
+      bool violates = false;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (!skip[r]) {
+          const float swr = ss[r].sw.x + ss[r].sw.y;
+          const float nx = __fdiv_rn(ss[r].sx.x + ss[r].sx.y, swr), ny = __fdiv_rn(ss[r].sy.x + ss[r].sy.y, swr),
+                      nz = __fdiv_rn(ss[r].sz.x + ss[r].sz.y, swr);
+          const float sh = __fsqrt_rn(torch_sqnorm(nx - cx[r], ny - cy[r], nz - cz[r]));
+          seeds[idx[r]] = make_float4(nx, ny, nz, sh);
+          violates |= !(sh < a.stop_thresh);
+          if (idx[r] == star) {
+            sm.star_pos = make_float4(nx, ny, nz, sh);
+            if (sh < a.eps_stat) sm.star_still = 1;
+          }
+        }
+      }
+      if (__any_sync(0xffffffffu, violates) && (t & 31) == 0) sm.violated[it % 3] = 1;
+    }
+    __syncthreads();
+    const bool viol = sm.violated[it % 3] != 0, still = sm.star_still != 0;
+    if (!viol || still) { T = it; break; }   // the reference's T, or the returned seed is stationary (block-uniform)
+  }
+  if (t == 0) {
+    // the star's latest position is C after exactly T iterations (every seed is swept at iteration 1)
+    const float4 c = sm.star_pos;
+    const float4 o = a.pts[start + star];
+    a.ctr[f] = make_float4(c.x + o.x, c.y + o.y, c.z + o.z, static_cast<float>(T));
+    a.iters[f] = T;
+    a.done[f] = 1;
+  }
+}
+
 __global__ void __launch_bounds__(kMsThreads, 3) ms_iterate_kernel(MsArgs a) {
   extern __shared__ __align__(16) unsigned char ms_smem_raw[];
   MsIterSmem &sm = *reinterpret_cast<MsIterSmem *>(ms_smem_raw);
@@ -1058,6 +1179,14 @@ int meanshift_launch(const float4 *pts, const int *fit_start, const int *fit_cou
                             "ms_witness smem attr");
       ms_witness_kernel<<<nf, kMsThreads, sizeof(MsWitSmem), st>>>(a);
       if ((rc = check_launch("ms_witness_kernel")) != PVN3D_OK) return rc;
+      static PerDeviceOnce once_fb;
+      PVN3D_ONCE_PER_DEVICE(once_fb,
+                            cudaFuncSetAttribute(ms_fallback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)sizeof(MsFbSmem)),
+                            "ms_fallback smem attr");
+      ms_fallback_kernel<<<nf, kMsThreads, sizeof(MsFbSmem), st>>>(a);
+      if ((rc = check_launch("ms_fallback_kernel")) != PVN3D_OK) return rc;
+      continue;   // no cooperative launch in this mode
     }
     void *kargs[] = {&a};
     PVN3D_CUDA_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(ms_iterate_kernel),

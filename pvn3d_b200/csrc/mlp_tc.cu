@@ -45,6 +45,10 @@ enum : int { PRO_DENSE = 0, PRO_SA_GATHER = 1, PRO_FP_INTERP = 2 };
 enum : int { EPI_STORE = 0, EPI_MAXPOOL = 1 };
 
 struct MlpArgs {
+  // W as a TMA tensor map ([n_pad][k_pad] fp32, box 32 columns x bn rows, SWIZZLE_128B): one
+  // cp.async.bulk.tensor.2d per K chunk lands the B operand in the UMMA layout (use_tma, else cp.async)
+  alignas(64) CUtensorMap tmap;
+  int use_tma;
   // GEMM
   const float *w;     // [n_pad][k_pad]
   const float *bias;  // [n_pad]
@@ -72,6 +76,7 @@ struct MlpArgs {
   int ldo, col0, relu;
   int round_out;  // store TF32-rounded values (the next layer then takes them with a_tf32)
   int pool;       // nsample of the max-pool epilogue (8, 16 or 32)
+  int reserve_sms;  // host only: SMs left to concurrent kernels (PVN3D_MLP_RESERVE_SMS in flags)
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
@@ -430,8 +435,11 @@ struct MlpSmemCtl {
 //              of the tensor core across tile boundaries;
 //   warp 12    issues the MMAs of tile j into accumulator j&1 of TMEM;
 //   epilogue   drains accumulator j&1 while the MMAs of tile j+1 fill the other one.
-template <int PRO, int EPI>
-__global__ void __launch_bounds__(kMlpThreads, 1) mlp_layer_kernel(const __grid_constant__ MlpArgs a) {
+// OCC = CTAs per SM the kernel is compiled for.  The layers are latency-bound (gathers through L2, TMEM
+// round trips) at 13 warps per SM; two co-resident CTAs (<= 78 registers per thread, half the operand ring,
+// two accumulators of <= 128 TMEM columns each) double the loads in flight for the narrow layers.
+template <int PRO, int EPI, int OCC>
+__global__ void __launch_bounds__(kMlpThreads, OCC) mlp_layer_kernel(const __grid_constant__ MlpArgs a) {
   extern __shared__ unsigned char mlp_smem_raw[];
   __shared__ MlpSmemCtl ctl;
   // 1024-byte aligned operand ring (SWIZZLE_128B atoms are 8 rows x 128 B)
@@ -514,9 +522,16 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_layer_kernel(const __grid_
         const uint32_t sa = ring + static_cast<uint32_t>(s) * stage_bytes;
         const uint32_t sb = sa + a_bytes;
         // weights: rows n0..n0+bn of W, columns kc*32..+32 (TF32-rounded, zero-padded): global -> smem
-        for (int i = pt; i < bn * 8; i += 128) {
-          const int n = i >> 3, c = i & 7;
-          cp_async16(sb + sw128_off(n, c), a.w + static_cast<size_t>(n0 + n) * a.k_pad + kc * 32 + c * 4);
+        if (a.use_tma) {
+          if (pt == 0) {   // one tensor-map copy, completing on the stage's `full` barrier in bytes
+            mbar_expect_tx_only(&ctl.full[s], static_cast<unsigned>(a.bn) * 128u);
+            tma_load_2d(sb, &a.tmap, kc * 32, n0, &ctl.full[s]);
+          }
+        } else {
+          for (int i = pt; i < bn * 8; i += 128) {
+            const int n = i >> 3, c = i & 7;
+            cp_async16(sb + sw128_off(n, c), a.w + static_cast<size_t>(n0 + n) * a.k_pad + kc * 32 + c * 4);
+          }
         }
         if (a_async) {
           const int k = kc * 32 + 4 * sub;
@@ -690,6 +705,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_layer_kernel(const __grid_
   }
 }
 
+bool weight_tensor_map(CUtensorMap *map, const float *w, int k_pad, int n_pad, int bn);   // below
+
 template <int PRO, int EPI>
 int launch_mlp(MlpArgs &a, cudaStream_t st) {
   if (a.rows <= 0) return PVN3D_OK;
@@ -701,18 +718,37 @@ int launch_mlp(MlpArgs &a, cudaStream_t st) {
   while (tc < a.bn) tc <<= 1;
   a.tmem_cols = tc;
   const size_t stage_bytes = kMlpBM * 128 + align_up(static_cast<size_t>(a.bn) * 128, 1024);
-  int stages = static_cast<int>((208 * 1024) / stage_bytes);
+  const int sms = std::max(1, sm_count() - a.reserve_sms);
+  const long long tiles = ((a.rows + kMlpBM - 1) / kMlpBM) * ceil_div(a.n_pad, a.bn);
+  // two CTAs per SM when both fit: accumulators 2 x 2 x tmem_cols <= 512 columns, >= 3 stages in half the
+  // shared memory, and enough tiles to feed twice the CTAs (PVN3D_MLP_OCC=1 forces one)
+  static const int occ_env = [] { const char *e = getenv("PVN3D_MLP_OCC"); return e ? atoi(e) : 0; }();
+  const size_t budget2 = (92 * 1024);   // ring of one of two co-resident CTAs (+17 KB control and staging each)
+  // asynchronous producers (pre-rounded dense activations) keep two chunks in flight: >= 3 stages
+  const size_t min_stages = (PRO == PRO_DENSE && a.a_tf32) ? 3 : 2;
+  bool occ2 = a.tmem_cols <= 128 && min_stages * stage_bytes <= budget2 && tiles >= 4ll * sms;
+  if (occ_env == 1) occ2 = false;
+  int stages = static_cast<int>((occ2 ? budget2 : size_t(208 * 1024)) / stage_bytes);
   if (stages > kMlpMaxStages) stages = kMlpMaxStages;
   if (stages < 2) stages = 2;
   a.stages = stages;
   const size_t smem = stages * stage_bytes + 1024 + kMlpEpiWarps * 4096;  // ring + epilogue staging
-  auto kern = mlp_layer_kernel<PRO, EPI>;
+  a.use_tma = weight_tensor_map(&a.tmap, a.w, a.k_pad, a.n_pad, a.bn) ? 1 : 0;
+  if (occ2) {
+    auto kern = mlp_layer_kernel<PRO, EPI, 2>;
+    static PerDeviceOnce once2;
+    PVN3D_ONCE_PER_DEVICE(once2,
+                          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024),
+                          "mlp smem attr (2 CTAs/SM)");
+    const unsigned grid = static_cast<unsigned>(std::min<long long>(tiles, 2ll * sms));
+    kern<<<grid, kMlpThreads, smem, st>>>(a);
+    return check_launch("mlp_layer_kernel<2>");
+  }
+  auto kern = mlp_layer_kernel<PRO, EPI, 1>;
   static PerDeviceOnce once;
   PVN3D_ONCE_PER_DEVICE(once,
                         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024),
                         "mlp smem attr");
-  const int sms = std::max(1, sm_count());
-  const long long tiles = ((a.rows + kMlpBM - 1) / kMlpBM) * ceil_div(a.n_pad, a.bn);
   const unsigned grid = static_cast<unsigned>(std::min<long long>(tiles, sms));
   kern<<<grid, kMlpThreads, smem, st>>>(a);
   return check_launch("mlp_layer_kernel");
@@ -733,6 +769,7 @@ int launch_mlp(MlpArgs &a, cudaStream_t st) {
 // the same item sequence, exactly like the per-layer kernel walks tiles: the operand ring and the two
 // TMEM accumulators are shared by all layers.  New dependency: the producers of (slot, l>0) wait on
 // h_ready[slot], on which the 128 epilogue threads arrive after storing (slot, l-1).
+constexpr int kChainMaxSlots = 8;
 struct ChainLayer {
   const float *w, *bias;
   int k_pad, n_pad, bn, n_blocks;
@@ -745,9 +782,10 @@ struct MlpChainArgs {
   MlpArgs base;        // producer of layer 0 + final epilogue (rows, out, ldo, col0, pool)
   ChainLayer layer[3];
   int n_layers;
-  float *scratch;      // [grid][2 slots][slot_floats]
+  float *scratch;      // [grid][n_slots][slot_floats]
   int h_off[2];        // float offset of layer l's output tile inside a slot (l < n_layers - 1)
   int slot_floats;
+  int n_slots;         // row tiles a CTA keeps in flight (2..kChainMaxSlots)
 };
 
 struct ChainSmemCtl {
@@ -755,8 +793,8 @@ struct ChainSmemCtl {
   uint64_t empty[kMlpMaxStages];
   uint64_t acc_full[2];
   uint64_t acc_empty[2];
-  uint64_t h_ready[2];            // 128 arrivals: epilogue threads, after storing a slot's intermediate tile
-  uint64_t h_seen[2];             // 256 arrivals: every producer thread, once it has passed a h_ready phase
+  uint64_t h_ready[kChainMaxSlots];   // 128 arrivals: epilogue threads, after storing a slot's intermediate tile
+  uint64_t h_seen[kChainMaxSlots];    // 256 arrivals: every producer thread, once it has passed a h_ready phase
   uint32_t tmem_base;
 };
 
@@ -777,10 +815,11 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_kernel(const __grid_
   const int S = a.stages;
   const int NL = c.n_layers;
   const long long row_tiles = (a.rows + kMlpBM - 1) / kMlpBM;
-  // row tiles of this CTA: blockIdx.x, +grid, ...; handled two at a time
+  // row tiles of this CTA: blockIdx.x, +grid, ...; handled NS at a time
+  const int NS = c.n_slots;
   const long long my_tiles = row_tiles > blockIdx.x ? (row_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const long long n_pairs = (my_tiles + 1) / 2;
-  float *const scratch = c.scratch + static_cast<size_t>(blockIdx.x) * 2 * c.slot_floats;
+  const long long n_pairs = (my_tiles + NS - 1) / NS;
+  float *const scratch = c.scratch + static_cast<size_t>(blockIdx.x) * NS * c.slot_floats;
 
   if (warp == kMlpEpiWarps + kMlpProWarps) {
     if (lane == 0) {
@@ -791,6 +830,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_kernel(const __grid_
       for (int b = 0; b < 2; ++b) {
         mbar_init(&ctl.acc_full[b], 1);
         mbar_init(&ctl.acc_empty[b], 128);
+      }
+      for (int b = 0; b < kChainMaxSlots; ++b) {
         mbar_init(&ctl.h_ready[b], 128);
         mbar_init(&ctl.h_seen[b], kMlpProWarps * 32);
       }
@@ -821,14 +862,14 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_kernel(const __grid_
     if (PRO == PRO_FP_INTERP)
       vec_ok = (a.c2 % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.known_feat) & 15u) == 0);
     int pend0 = 0, pend1 = 0, npend = 0;
-    unsigned hwaits[2] = {0u, 0u};
+    unsigned hwaits = 0u;   // bit `slot`: parity of the next h_ready phase this thread waits for
     long long it_base = 0;
     for (long long pair = 0; pair < n_pairs; ++pair) {
       for (int l = 0; l < NL; ++l) {
         const ChainLayer &L = c.layer[l];
         const int kc_total = L.k_pad / 32;
-        for (int slot = 0; slot < 2; ++slot) {
-          const long long local = 2 * pair + slot;
+        for (int slot = 0; slot < NS; ++slot) {
+          const long long local = NS * pair + slot;
           if (local >= my_tiles) continue;
           const long long rt = blockIdx.x + local * gridDim.x;
           const long long p_first = rt * kMlpBM + r_first;
@@ -847,8 +888,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_kernel(const __grid_
               if (npend == 2) mbar_arrive(&ctl.full[pend1]);
               npend = 0;
             }
-            mbar_wait(&ctl.h_ready[slot], hwaits[slot] & 1u);
-            ++hwaits[slot];
+            mbar_wait(&ctl.h_ready[slot], (hwaits >> slot) & 1u);
+            hwaits ^= 1u << slot;
             mbar_arrive(&ctl.h_seen[slot]);   // this phase has been observed: the epilogue may open the next one
             const float *h = scratch + static_cast<size_t>(slot) * c.slot_floats + c.h_off[l - 1];
             const int ld = c.layer[l - 1].n_pad;
@@ -928,14 +969,14 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_kernel(const __grid_
   } else if (warp < kMlpEpiWarps) {
     // ================= epilogue =========================================================================
     long long j = 0;
-    unsigned hsignals[2] = {0u, 0u};
+    unsigned hsig_any = 0u, hsig_par = 0u;   // per slot: signalled before / parity of the last phase signalled
     const uint32_t stg = ring + static_cast<uint32_t>(S) * stage_bytes + warp * 4096u;
     for (long long pair = 0; pair < n_pairs; ++pair) {
       for (int l = 0; l < NL; ++l) {
         const ChainLayer &L = c.layer[l];
         const bool last = l == NL - 1;
-        for (int slot = 0; slot < 2; ++slot) {
-          const long long local = 2 * pair + slot;
+        for (int slot = 0; slot < NS; ++slot) {
+          const long long local = NS * pair + slot;
           if (local >= my_tiles) continue;
           const long long rt = blockIdx.x + local * gridDim.x;
           const long long p0 = rt * kMlpBM;
@@ -1033,8 +1074,10 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_kernel(const __grid_
             __threadfence();
             // phase k of h_ready[slot] may only complete once every producer thread has observed phase k-1
             // (a parity wait cannot tell phase k-1 from phase k+1)
-            if (hsignals[slot] > 0) mbar_wait(&ctl.h_seen[slot], (hsignals[slot] - 1u) & 1u);
-            ++hsignals[slot];
+            if ((hsig_any >> slot) & 1u) mbar_wait(&ctl.h_seen[slot], (hsig_par >> slot) & 1u);
+            else hsig_par |= 1u << slot;       // first signal: the next wait is for phase 0 -> parity 0 after the toggle
+            hsig_any |= 1u << slot;
+            hsig_par ^= 1u << slot;
             mbar_arrive(&ctl.h_ready[slot]);
           }
         }
@@ -1047,8 +1090,8 @@ __global__ void __launch_bounds__(kMlpThreads, 1) mlp_chain_kernel(const __grid_
       for (int l = 0; l < NL; ++l) {
         const ChainLayer &L = c.layer[l];
         const int kc_total = L.k_pad / 32;
-        for (int slot = 0; slot < 2; ++slot) {
-          if (2 * pair + slot >= my_tiles) continue;
+        for (int slot = 0; slot < NS; ++slot) {
+          if (NS * pair + slot >= my_tiles) continue;
           for (int nb = 0; nb < L.n_blocks; ++nb, ++j, it_base += kc_total) {
             const int bn = min(L.bn, L.n_pad - nb * L.bn);
             const uint32_t idesc = instr_desc_tf32(bn);
@@ -1132,24 +1175,23 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// tensor maps of the chain's weight matrices; false -> the kernel falls back to per-thread cp.async
-bool chain_tensor_maps(MlpChainArgs &c) {
+// tensor map of one weight matrix; false -> the kernel falls back to per-thread cp.async
+bool weight_tensor_map(CUtensorMap *map, const float *w, int k_pad, int n_pad, int bn) {
   const char *env = getenv("PVN3D_MLP_TMA");
   if (env && env[0] == '0') return false;
   EncodeTiledFn enc = encode_tiled_fn();
-  if (!enc) return false;
-  for (int l = 0; l < c.n_layers; ++l) {
-    const ChainLayer &L = c.layer[l];
-    if (reinterpret_cast<uintptr_t>(L.w) & 15u) return false;
-    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(L.k_pad), static_cast<cuuint64_t>(L.n_pad)};
-    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(L.k_pad) * sizeof(float)};
-    const cuuint32_t box[2] = {32u, static_cast<cuuint32_t>(L.bn)};
-    const cuuint32_t estr[2] = {1u, 1u};
-    const CUresult r = enc(&c.tmap[l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(L.w), dims,
-                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return false;
-  }
+  if (!enc || (reinterpret_cast<uintptr_t>(w) & 15u)) return false;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(k_pad), static_cast<cuuint64_t>(n_pad)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(k_pad) * sizeof(float)};
+  const cuuint32_t box[2] = {32u, static_cast<cuuint32_t>(bn)};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(w), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+bool chain_tensor_maps(MlpChainArgs &c) {
+  for (int l = 0; l < c.n_layers; ++l)
+    if (!weight_tensor_map(&c.tmap[l], c.layer[l].w, c.layer[l].k_pad, c.layer[l].n_pad, c.layer[l].bn)) return false;
   return true;
 }
 
@@ -1163,6 +1205,18 @@ bool chain_layers_ok(const pvn3d_mlp_layer_t *layers, int n_layers, int k_first_
     if (l > 0 && layers[l].k_pad < layers[l - 1].n_pad) return false;
   }
   return layers[0].k_pad >= k_first_min;
+}
+
+// row tiles a CTA keeps in flight: enough to cover the epilogue -> L2 -> producer latency of a layer
+// transition, as long as all scratch tiles of the grid stay well inside the 126 MB L2 (<= 48 MB)
+int chain_slots(int slot_floats, long long row_tiles, unsigned grid) {
+  int want = 4;
+  if (const char *env = getenv("PVN3D_CHAIN_SLOTS")) want = atoi(env);
+  want = std::max(2, std::min(kChainMaxSlots, want));
+  const long long per_cta = (row_tiles + grid - 1) / std::max(1u, grid);
+  while (want > 2 && want > per_cta) --want;
+  while (want > 2 && static_cast<size_t>(grid) * want * slot_floats * sizeof(float) > (48u << 20)) --want;
+  return want;
 }
 
 template <int PRO, int EPI>
@@ -1180,10 +1234,11 @@ int launch_chain(MlpChainArgs &c, void *workspace, size_t workspace_bytes, cudaS
   PVN3D_ONCE_PER_DEVICE(once,
                         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024),
                         "mlp chain smem attr");
-  const int sms = std::max(1, sm_count());
+  const int sms = std::max(1, sm_count() - a.reserve_sms);
   const long long row_tiles = (a.rows + kMlpBM - 1) / kMlpBM;
   const unsigned grid = static_cast<unsigned>(std::min<long long>(row_tiles, sms));
-  const size_t need = static_cast<size_t>(grid) * 2 * c.slot_floats * sizeof(float);
+  c.n_slots = chain_slots(c.slot_floats, row_tiles, grid);
+  const size_t need = static_cast<size_t>(grid) * c.n_slots * c.slot_floats * sizeof(float);
   if (c.n_layers > 1 && (!workspace || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15u)))
     return PVN3D_ERR_WORKSPACE;
   c.scratch = static_cast<float *>(workspace);
@@ -1238,6 +1293,7 @@ extern "C" int pvn3d_mlp_dense(const float *a, int lda, int a_cols, long long ro
   m.out = out; m.ldo = ldo; m.col0 = col0;
   m.relu = flags & PVN3D_MLP_RELU; m.round_out = (flags & PVN3D_MLP_ROUND_OUT) && !pool;
   m.a_tf32 = (flags & PVN3D_MLP_A_TF32) ? 1 : 0;
+  m.reserve_sms = (flags >> 8) & 0xff;
   return dispatch(m, PRO_DENSE, pool, as_stream(stream));
 }
 
@@ -1259,6 +1315,7 @@ extern "C" int pvn3d_mlp_sa_first(const float *xyz, const float *new_xyz, const 
   a.n = n; a.m = m; a.ns = ns;
   a.out = out; a.ldo = ldo; a.col0 = col0;
   a.relu = flags & PVN3D_MLP_RELU; a.round_out = (flags & PVN3D_MLP_ROUND_OUT) ? 1 : 0;
+  a.reserve_sms = (flags >> 8) & 0xff;
   return dispatch(a, PRO_SA_GATHER, pool, as_stream(stream));
 }
 
@@ -1279,6 +1336,7 @@ extern "C" int pvn3d_mlp_fp_first(const float *known_feat_pm, int c2, const int 
   a.lds = lds; a.c1 = c1; a.n_unknown = n_unknown; a.m_known = m_known;
   a.out = out; a.ldo = ldo; a.col0 = col0;
   a.relu = flags & PVN3D_MLP_RELU; a.round_out = (flags & PVN3D_MLP_ROUND_OUT) ? 1 : 0;
+  a.reserve_sms = (flags >> 8) & 0xff;
   return dispatch(a, PRO_FP_INTERP, 0, as_stream(stream));
 }
 
@@ -1295,13 +1353,13 @@ extern "C" size_t pvn3d_mlp_chain_workspace_bytes(const pvn3d_mlp_layer_t *layer
   if (!layers || n_layers < 1 || n_layers > 3) return 0;
   size_t floats = 0;
   for (int l = 0; l + 1 < n_layers; ++l) floats += static_cast<size_t>(kMlpBM) * layers[l].n_pad;
-  return static_cast<size_t>(std::max(1, sm_count())) * 2 * floats * sizeof(float) + 256;
+  return static_cast<size_t>(std::max(1, sm_count())) * kChainMaxSlots * floats * sizeof(float) + 256;
 }
 
 extern "C" int pvn3d_mlp_sa_chain(const float *xyz, const float *new_xyz, const float *feat_pm, int ldf,
                                   int c_feat, const int *idx, int b, int n, int m, int ns,
-                                  const pvn3d_mlp_layer_t *layers, int n_layers, int pool, float *out,
-                                  int ldo, int col0, void *workspace, size_t workspace_bytes,
+                                  const pvn3d_mlp_layer_t *layers, int n_layers, int flags, int pool,
+                                  float *out, int ldo, int col0, void *workspace, size_t workspace_bytes,
                                   pvn3d_stream_t stream) {
   if (!xyz || !new_xyz || !idx || !out || b < 0 || n <= 0 || m < 0 || ns <= 0 || c_feat < 0 ||
       (c_feat > 0 && (!feat_pm || ldf < c_feat)) || ldo % 4 || col0 % 4 ||
@@ -1318,6 +1376,7 @@ extern "C" int pvn3d_mlp_sa_chain(const float *xyz, const float *new_xyz, const 
   a.xyz = xyz; a.new_xyz = new_xyz; a.feat = feat_pm; a.ldf = ldf; a.c_feat = c_feat; a.idx = idx;
   a.n = n; a.m = m; a.ns = ns;
   a.out = out; a.ldo = ldo; a.col0 = col0; a.relu = 1; a.round_out = 0; a.pool = pool;
+  a.reserve_sms = (flags >> 8) & 0xff;
   a.k_pad = layers[0].k_pad;
   chain_plan(c, layers, n_layers);
   if (pool) return launch_chain<PRO_SA_GATHER, EPI_MAXPOOL>(c, workspace, workspace_bytes, as_stream(stream));
@@ -1326,7 +1385,7 @@ extern "C" int pvn3d_mlp_sa_chain(const float *xyz, const float *new_xyz, const 
 
 extern "C" int pvn3d_mlp_fp_chain(const float *known_feat_pm, int c2, const int *nn_idx, const float *nn_w,
                                   const float *skip_pm, int lds, int c1, int b, int n_unknown,
-                                  int m_known, const pvn3d_mlp_layer_t *layers, int n_layers,
+                                  int m_known, const pvn3d_mlp_layer_t *layers, int n_layers, int flags,
                                   float *out, int ldo, int col0, void *workspace, size_t workspace_bytes,
                                   pvn3d_stream_t stream) {
   if (!known_feat_pm || !nn_idx || !nn_w || !out || b < 0 || n_unknown < 0 || m_known <= 0 || c2 <= 0 ||
@@ -1341,6 +1400,7 @@ extern "C" int pvn3d_mlp_fp_chain(const float *known_feat_pm, int c2, const int 
   a.known_feat = known_feat_pm; a.c2 = c2; a.nn_idx = nn_idx; a.nn_w = nn_w; a.skip = skip_pm;
   a.lds = lds; a.c1 = c1; a.n_unknown = n_unknown; a.m_known = m_known;
   a.out = out; a.ldo = ldo; a.col0 = col0; a.relu = 1; a.round_out = 0; a.pool = 0;
+  a.reserve_sms = (flags >> 8) & 0xff;
   a.k_pad = layers[0].k_pad;
   chain_plan(c, layers, n_layers);
   return launch_chain<PRO_FP_INTERP, EPI_STORE>(c, workspace, workspace_bytes, as_stream(stream));

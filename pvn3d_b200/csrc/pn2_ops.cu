@@ -370,6 +370,29 @@ int channel_slices(int c, int other_ctas) {
 
 using namespace pvn3d;
 
+// new_xyz[b, j, :] = xyz[b, idx[b, j], :] -- what the reference spells
+// gather_operation(xyz.transpose(1,2).contiguous(), idx).transpose(1,2).contiguous() (pointnet2_modules.py:47-53)
+__global__ void gather_xyz_kernel(const float *__restrict__ xyz, const int *__restrict__ idx, int n, long long total,
+                                  int m, float *__restrict__ out) {
+  const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  const long long b = p / m;
+  const float *src = xyz + (b * n + idx[p]) * 3;
+  out[p * 3 + 0] = __ldg(src + 0);
+  out[p * 3 + 1] = __ldg(src + 1);
+  out[p * 3 + 2] = __ldg(src + 2);
+}
+
+extern "C" int pvn3d_gather_xyz(const float *xyz, const int *idx, int b, int n, int m, float *out,
+                                pvn3d_stream_t stream) {
+  if (!xyz || !idx || !out || b < 0 || n <= 0 || m < 0) return PVN3D_ERR_INVALID_ARG;
+  const long long total = static_cast<long long>(b) * m;
+  if (total == 0) return PVN3D_OK;
+  gather_xyz_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, as_stream(stream)>>>(xyz, idx, n, total, m,
+                                                                                               out);
+  return check_launch("gather_xyz_kernel");
+}
+
 extern "C" int pvn3d_gather_points(const float *points, const int *idx, int b, int c, int n, int m,
                                    float *out, pvn3d_stream_t stream) {
   if (!points || !idx || !out || b < 0 || c < 0 || n <= 0 || m < 0) return PVN3D_ERR_INVALID_ARG;

@@ -67,8 +67,10 @@ class PackedLayer:
 MLP_RELU, MLP_ROUND_OUT, MLP_A_TF32 = 1, 2, 4      # include/pvn3d_b200.h PVN3D_MLP_*
 
 
-def _flags(relu, round_out=False, a_tf32=False):
-    return (MLP_RELU if relu else 0) | (MLP_ROUND_OUT if round_out else 0) | (MLP_A_TF32 if a_tf32 else 0)
+def _flags(relu, round_out=False, a_tf32=False, reserve=0):
+    """PVN3D_MLP_* flags; reserve = SMs left to concurrent kernels (PVN3D_MLP_RESERVE_SMS)"""
+    return ((MLP_RELU if relu else 0) | (MLP_ROUND_OUT if round_out else 0) | (MLP_A_TF32 if a_tf32 else 0)
+            | ((int(reserve) & 0xFF) << 8))
 
 
 def _stream(dev):
@@ -76,7 +78,7 @@ def _stream(dev):
 
 
 def mlp_dense(a2d: torch.Tensor, layer: PackedLayer, relu=True, pool=0, out=None, col0=0, round_out=False,
-              a_tf32=False):
+              a_tf32=False, reserve=0):
     """a2d [rows, lda] point-major activations (all lda columns valid or zero).  a_tf32: a2d came out of
     a layer run with round_out=True (values already TF32) -> asynchronous copy path."""
     lib = _lib.load()
@@ -85,13 +87,13 @@ def mlp_dense(a2d: torch.Tensor, layer: PackedLayer, relu=True, pool=0, out=None
         out = torch.empty((rows // pool if pool else rows, layer.n_pad), dtype=torch.float32, device=a2d.device)
     with torch.cuda.device(a2d.device):
         rc = lib.pvn3d_mlp_dense(ptr(a2d), lda, lda, rows, ptr(layer.w), ptr(layer.bias), layer.k_pad, layer.n_pad,
-                                 _flags(relu, round_out, a_tf32), pool, ptr(out), out.size(-1), col0, _stream(a2d.device))
+                                 _flags(relu, round_out, a_tf32, reserve), pool, ptr(out), out.size(-1), col0, _stream(a2d.device))
     check(rc, "pvn3d_mlp_dense")
     return out
 
 
 def mlp_sa_first(xyz, new_xyz, feat_pm, ldf, c_feat, idx, layer: PackedLayer, relu=True, pool=0, out=None, col0=0,
-                 round_out=False):
+                 round_out=False, reserve=0):
     lib = _lib.load()
     b, n = xyz.shape[0], xyz.shape[1]
     m, ns = idx.shape[1], idx.shape[2]
@@ -100,21 +102,22 @@ def mlp_sa_first(xyz, new_xyz, feat_pm, ldf, c_feat, idx, layer: PackedLayer, re
         out = torch.empty((rows // pool if pool else rows, layer.n_pad), dtype=torch.float32, device=xyz.device)
     with torch.cuda.device(xyz.device):
         rc = lib.pvn3d_mlp_sa_first(ptr(xyz), ptr(new_xyz), feat_pm, ldf, c_feat, ptr(idx), b, n, m, ns, ptr(layer.w),
-                                    ptr(layer.bias), layer.k_pad, layer.n_pad, _flags(relu, round_out), pool, ptr(out),
+                                    ptr(layer.bias), layer.k_pad, layer.n_pad, _flags(relu, round_out, reserve=reserve), pool, ptr(out),
                                     out.size(-1), col0, _stream(xyz.device))
     check(rc, "pvn3d_mlp_sa_first")
     return out
 
 
-def mlp_fp_first(known_feat_pm, nn_idx, nn_w, skip_ptr, lds, c1, layer: PackedLayer, relu=True, round_out=False):
+def mlp_fp_first(known_feat_pm, nn_idx, nn_w, skip_ptr, lds, c1, layer: PackedLayer, relu=True, round_out=False, reserve=0):
     lib = _lib.load()
     b, m_known, c2 = known_feat_pm.shape
     n_unknown = nn_idx.shape[1]
     out = torch.empty((b * n_unknown, layer.n_pad), dtype=torch.float32, device=known_feat_pm.device)
     with torch.cuda.device(known_feat_pm.device):
         rc = lib.pvn3d_mlp_fp_first(ptr(known_feat_pm), c2, ptr(nn_idx), ptr(nn_w), skip_ptr, lds, c1, b, n_unknown,
-                                    m_known, ptr(layer.w), ptr(layer.bias), layer.k_pad, layer.n_pad, _flags(relu, round_out),
-                                    ptr(out), out.size(-1), 0, _stream(known_feat_pm.device))
+                                    m_known, ptr(layer.w), ptr(layer.bias), layer.k_pad, layer.n_pad,
+                                    _flags(relu, round_out, reserve=reserve), ptr(out), out.size(-1), 0,
+                                    _stream(known_feat_pm.device))
     check(rc, "pvn3d_mlp_fp_first")
     return out
 
@@ -139,7 +142,7 @@ class LayerChain:
         return ctypes.addressof(self.arr)
 
 
-def mlp_sa_chain(xyz, new_xyz, feat_pm, ldf, c_feat, idx, chain: LayerChain, pool=0, out=None, col0=0):
+def mlp_sa_chain(xyz, new_xyz, feat_pm, ldf, c_feat, idx, chain: LayerChain, pool=0, out=None, col0=0, reserve=0):
     """a whole SA-scale SharedMLP (QueryAndGroup producer -> layers -> max-pool) in one launch"""
     lib = _lib.load()
     b, n = xyz.shape[0], xyz.shape[1]
@@ -149,12 +152,13 @@ def mlp_sa_chain(xyz, new_xyz, feat_pm, ldf, c_feat, idx, chain: LayerChain, poo
         out = torch.empty((rows // pool if pool else rows, chain.layers[-1].n_pad), dtype=torch.float32, device=xyz.device)
     with torch.cuda.device(xyz.device):
         rc = lib.pvn3d_mlp_sa_chain(ptr(xyz), ptr(new_xyz), feat_pm, ldf, c_feat, ptr(idx), b, n, m, ns, chain.ptr, chain.n,
-                                    pool, ptr(out), out.size(-1), col0, chain.ws_ptr, chain.ws_bytes, _stream(xyz.device))
+                                    _flags(True, reserve=reserve), pool, ptr(out), out.size(-1), col0, chain.ws_ptr,
+                                    chain.ws_bytes, _stream(xyz.device))
     check(rc, "pvn3d_mlp_sa_chain")
     return out
 
 
-def mlp_fp_chain(known_feat_pm, nn_idx, nn_w, skip_ptr, lds, c1, chain: LayerChain, out=None):
+def mlp_fp_chain(known_feat_pm, nn_idx, nn_w, skip_ptr, lds, c1, chain: LayerChain, out=None, reserve=0):
     """a whole FP-module SharedMLP (three_interpolate + concat producer -> layers) in one launch"""
     lib = _lib.load()
     b, m_known, c2 = known_feat_pm.shape
@@ -163,8 +167,8 @@ def mlp_fp_chain(known_feat_pm, nn_idx, nn_w, skip_ptr, lds, c1, chain: LayerCha
         out = torch.empty((b * n_unknown, chain.layers[-1].n_pad), dtype=torch.float32, device=known_feat_pm.device)
     with torch.cuda.device(known_feat_pm.device):
         rc = lib.pvn3d_mlp_fp_chain(ptr(known_feat_pm), c2, ptr(nn_idx), ptr(nn_w), skip_ptr, lds, c1, b, n_unknown, m_known,
-                                    chain.ptr, chain.n, ptr(out), out.size(-1), 0, chain.ws_ptr, chain.ws_bytes,
-                                    _stream(known_feat_pm.device))
+                                    chain.ptr, chain.n, _flags(True, reserve=reserve), ptr(out), out.size(-1), 0, chain.ws_ptr,
+                                    chain.ws_bytes, _stream(known_feat_pm.device))
     check(rc, "pvn3d_mlp_fp_chain")
     return out
 
@@ -179,15 +183,34 @@ def three_nn_weights(dist2: torch.Tensor) -> torch.Tensor:
     return w
 
 
+class GeoPlan:
+    """the coordinate-only half of one Pointnet2MSG.forward (FusedPointnet2MSG.geometry)"""
+
+    def __init__(self, cloud: torch.Tensor, l_xyz: List[torch.Tensor]):
+        self.key = (cloud.data_ptr(), tuple(cloud.shape))
+        self.l_xyz = l_xyz                       # xyz of levels 0..4
+        self.ball: List[Tuple[torch.Tensor, torch.Tensor]] = []     # per SA level: idx of both radii
+        self.nn: Dict[int, Tuple[torch.Tensor, torch.Tensor]] = {}  # per FP level: (idx [B,n,3], weights [B,n,3])
+        self.done = None                          # event recorded by whoever computed the plan on a side stream
+
+    def tensors(self):
+        for t in self.l_xyz:
+            yield t
+        # (ball / nn tables are computed on the consumer's stream: FusedPointnet2MSG.queries)
+
+
 class FusedPointnet2MSG:
     """Inference engine for Pointnet2MSG on libpvn3d_b200 only (see module docstring)."""
 
     def __init__(self, model: torch.nn.Module, device="cuda", chain: bool | None = None):
         self.dev = torch.device(device)
-        #: chain=True: one launch per SharedMLP (inter-layer tiles stay in L2); False: one launch per layer.
-        #: Same bits either way (tests/test_mlp_gpu.py); PVN3D_MLP_CHAIN=0 selects the per-layer launches.
+        #: chain=True: one launch per SharedMLP (inter-layer tiles stay in L2, DRAM traffic of the MLPs -95 %);
+        #: False (default): one launch per layer.  Same bits either way (tests/test_mlp_gpu.py).  Measured on B200
+        #: the chained kernel is 11 % SLOWER (5.25 vs 4.72 ms per 32-frame batch, DESIGN.md section 9): with 13 warps
+        #: per SM the layers are latency-bound, not HBM-bound, and the chain adds a dependency per layer.
+        #: PVN3D_MLP_CHAIN=1 selects it.
         if chain is None:
-            chain = os.environ.get("PVN3D_MLP_CHAIN", "1") != "0"
+            chain = os.environ.get("PVN3D_MLP_CHAIN", "0") == "1"
         self.chain = bool(chain)
         model = model.to(self.dev).eval()
         self.sa: List[List[List[PackedLayer]]] = []
@@ -251,62 +274,105 @@ class FusedPointnet2MSG:
         return {k: statistics.median(r.get(k, 0.0) for r in runs) for k in runs[0]}
 
     @torch.no_grad()
-    def forward(self, pointcloud: torch.Tensor) -> torch.Tensor:
-        """pointcloud [B,N,3+C] f32 contiguous on device -> features [B,128,N] (as the reference returns)"""
+    def sampling(self, pointcloud: torch.Tensor, fps_chunk: int = 0) -> "GeoPlan":
+        """The four furthest-point samplings of Pointnet2MSG.forward and the sampled centres (reference
+        pointnet2_modules.py:44-53): 3708 dependent arg-max iterations on ONE CTA per frame -- latency-bound
+        and narrow (B of the 148 SMs).  They depend on the coordinates only, so FramePipeline runs them for
+        batch i+1 on a side stream under the shared MLPs of batch i.
+        fps_chunk > 0: sample that many frames per launch, so that a caller who keeps only `fps_chunk` SMs free
+        for this stream never has more sampling CTAs pending than free SMs."""
         assert pointcloud.is_cuda and pointcloud.is_contiguous() and pointcloud.dtype == torch.float32
+        b = pointcloud.size(0)
+        xyz = pointcloud[..., :3].contiguous()
+        self._m("glue")
+        plan = GeoPlan(pointcloud, [xyz])
+        lib = _lib.load()
+        for li, (npoint, radii, nsamples, _) in enumerate(SA_SPEC):
+            x = plan.l_xyz[-1]
+            if fps_chunk and fps_chunk < b:
+                fidx = torch.empty((b, npoint), dtype=torch.int32, device=self.dev)
+                n = x.size(1)
+                with torch.cuda.device(self.dev):
+                    for f0 in range(0, b, fps_chunk):
+                        nb = min(fps_chunk, b - f0)
+                        check(lib.pvn3d_furthest_point_sampling(x.data_ptr() + f0 * n * 12, nb, n, npoint,
+                                                                fidx.data_ptr() + f0 * npoint * 4, _stream(self.dev)),
+                              "pvn3d_furthest_point_sampling")
+            else:
+                fidx = _ext.furthest_point_sampling(x, npoint)
+            self._m("fps")
+            plan.l_xyz.append(_ext.gather_xyz(x, fidx))
+            self._m("glue")
+        return plan
+
+    @torch.no_grad()
+    def queries(self, plan: "GeoPlan") -> "GeoPlan":
+        """The wide coordinate-only kernels: ball queries of both radii of every SA level and the 3-NN indices +
+        inverse-distance weights of every FP level (pointnet2_modules.py:57-60,183-186).  They fill the machine,
+        so they run on the stream of the MLPs (0.9 ms per 32-frame batch)."""
+        for li, (npoint, radii, nsamples, _) in enumerate(SA_SPEC):
+            plan.ball.append(_ext.ball_query2(plan.l_xyz[li + 1], plan.l_xyz[li], radii, nsamples))   # both radii, one pass
+        self._m("ball")
+        for i in range(3, -1, -1):
+            d2, nn_idx = _ext.three_nn(plan.l_xyz[i], plan.l_xyz[i + 1])
+            plan.nn[i] = (nn_idx, three_nn_weights(d2))
+        self._m("three_nn")
+        return plan
+
+    def geometry(self, pointcloud: torch.Tensor, fps_chunk: int = 0) -> "GeoPlan":
+        """everything of the forward pass that depends on the coordinates only"""
+        return self.queries(self.sampling(pointcloud, fps_chunk))
+
+    @torch.no_grad()
+    def features(self, pointcloud: torch.Tensor, plan: "GeoPlan", reserve_sms: int = 0) -> torch.Tensor:
+        """The shared MLPs of all SA / FP levels on a geometry plan -> [B,128,N].  reserve_sms: SMs the persistent
+        MLP kernels leave free for kernels of other streams (the next batch's sampling)."""
         b, n0, width = pointcloud.shape
         c0 = width - 3
-        xyz = pointcloud[..., :3].contiguous()
+        rs = int(reserve_sms)
+        if not plan.ball:
+            self.queries(plan)
         # level-0 descriptors are columns 3.. of the input rows themselves (point-major already)
         feats: List[Tuple[int, int, int]] = [(pointcloud.data_ptr() + 12, width, c0)]   # (address, ld, channels)
         keep = [pointcloud]
-        l_xyz = [xyz]
+        l_xyz = plan.l_xyz
         for li, (npoint, radii, nsamples, _) in enumerate(SA_SPEC):
-            x = l_xyz[-1]
+            x, new_xyz = l_xyz[li], l_xyz[li + 1]
             fptr, ldf, c_feat = feats[-1]
-            fidx = _ext.furthest_point_sampling(x, npoint)
-            self._m("fps")
-            new_xyz = torch.gather(x, 1, fidx.long().unsqueeze(-1).expand(-1, -1, 3)).contiguous()
             out_l = torch.empty((b, npoint, self.sa_out[li]), dtype=torch.float32, device=self.dev)
             col = 0
-            self._m("glue")
-            idxs = _ext.ball_query2(new_xyz, x, radii, nsamples)    # one pass over the cloud for both radii
-            self._m("ball")
-            for si, (idx, ns, layers) in enumerate(zip(idxs, nsamples, self.sa[li])):
+            for si, (idx, ns, layers) in enumerate(zip(plan.ball[li], nsamples, self.sa[li])):
                 if self.chain:
                     mlp_sa_chain(x, new_xyz, fptr, ldf, c_feat, idx, self.sa_chain[li][si], pool=ns,
-                                 out=out_l.view(b * npoint, -1), col0=col)
+                                 out=out_l.view(b * npoint, -1), col0=col, reserve=rs)
                     col += layers[-1].n
                     continue
                 # intermediates are stored TF32-rounded (what the next layer's operand is anyway)
-                h = mlp_sa_first(x, new_xyz, fptr, ldf, c_feat, idx, layers[0], round_out=True)
+                h = mlp_sa_first(x, new_xyz, fptr, ldf, c_feat, idx, layers[0], round_out=True, reserve=rs)
                 for mid in layers[1:-1]:
-                    h = mlp_dense(h, mid, round_out=True, a_tf32=True)
-                mlp_dense(h, layers[-1], pool=ns, out=out_l.view(b * npoint, -1), col0=col, a_tf32=True)
+                    h = mlp_dense(h, mid, round_out=True, a_tf32=True, reserve=rs)
+                mlp_dense(h, layers[-1], pool=ns, out=out_l.view(b * npoint, -1), col0=col, a_tf32=True, reserve=rs)
                 col += layers[-1].n
             self._m("mlp")
-            l_xyz.append(new_xyz)
             feats.append((out_l.data_ptr(), out_l.size(-1), out_l.size(-1)))
             keep.append(out_l)
         # feature propagation, deepest first (pvn3d.py:149-152)
         l_feat = list(keep)            # l_feat[i]: tensor owning level i's descriptors (point-major)
         for i in range(3, -1, -1):
             unknown, known = l_xyz[i], l_xyz[i + 1]
-            d2, nn_idx = _ext.three_nn(unknown, known)
-            nn_w = three_nn_weights(d2)
-            self._m("three_nn")
+            nn_idx, nn_w = plan.nn[i]
             known_feat = l_feat[i + 1]
             if known_feat.dim() == 2:
                 known_feat = known_feat.view(b, known.size(1), -1)
             sptr, lds, c1 = feats[i]
             layers = self.fp[i]
             if self.chain:
-                h = mlp_fp_chain(known_feat, nn_idx, nn_w, sptr, lds, c1, self.fp_chain[i])
+                h = mlp_fp_chain(known_feat, nn_idx, nn_w, sptr, lds, c1, self.fp_chain[i], reserve=rs)
             else:
-                h = mlp_fp_first(known_feat, nn_idx, nn_w, sptr, lds, c1, layers[0], round_out=True)
+                h = mlp_fp_first(known_feat, nn_idx, nn_w, sptr, lds, c1, layers[0], round_out=True, reserve=rs)
                 for li2, lyr in enumerate(layers[1:]):
                     last = li2 == len(layers) - 2        # level tables stay full fp32
-                    h = mlp_dense(h, lyr, round_out=not last, a_tf32=True)
+                    h = mlp_dense(h, lyr, round_out=not last, a_tf32=True, reserve=rs)
             l_feat[i] = h.view(b, unknown.size(1), -1)
             feats[i] = (h.data_ptr(), h.size(-1), h.size(-1))
             self._m("mlp")
@@ -317,5 +383,10 @@ class FusedPointnet2MSG:
         out = _ext.transpose_nc_to_cn(out_pm)
         self._m("glue")
         return out
+
+    @torch.no_grad()
+    def forward(self, pointcloud: torch.Tensor) -> torch.Tensor:
+        """pointcloud [B,N,3+C] f32 contiguous on device -> features [B,128,N] (as the reference returns)"""
+        return self.features(pointcloud, self.geometry(pointcloud))
 
     __call__ = forward

@@ -25,7 +25,7 @@ class FramePipeline:
     def __init__(self, shape: str, batch: int, n_points: int = fixtures.N_SAMPLE_POINTS, device="cuda",
                  lm_obj_id: int = 1, early_exit: bool = False, model: Optional[torch.nn.Module] = None,
                  allow_tf32: bool = True, engine: str = "fused", ms_mode: Optional[str] = None,
-                 overlap: bool = True, bandwidth: float = 0.08):
+                 overlap: bool = True, bandwidth: float = 0.08, fps_chunk: int = 16, pose_stream: bool = True):
         self.dev = torch.device(device)
         self.shape, self.b, self.n, self.k = shape, int(batch), int(n_points), fixtures.N_KEYPOINTS
         self.model = (model if model is not None else seeded_pointnet2msg(0, 1)).to(self.dev).eval()
@@ -62,7 +62,17 @@ class FramePipeline:
         #: heads, synthetic here): it runs on its own stream, so its many small kernels fill the SMs that the
         #: latency-bound furthest-point sampling of path A (one CTA per frame) leaves idle
         self.overlap = bool(overlap)
-        self._pose_stream = torch.cuda.Stream(self.dev) if self.overlap else None
+        self._pose_stream = torch.cuda.Stream(self.dev) if (self.overlap and pose_stream) else None
+        #: look-ahead: when the caller names the NEXT batch (run_device(..., next_cloud=) / run_host(hb, next_hb)),
+        #: its coordinate-only half of hot path A (furthest-point sampling: 3708 dependent iterations on one CTA
+        #: per frame, plus ball queries and 3-NN) runs on a third stream UNDER the shared MLPs of the current
+        #: batch.  The sampling kernels are launched `fps_chunk` frames at a time and the persistent MLP kernels
+        #: leave that many SMs free (PVN3D_MLP_RESERVE_SMS), so neither side ever waits for an SM.
+        self.fps_chunk = max(1, min(int(fps_chunk), self.b))
+        self._geo_stream = torch.cuda.Stream(self.dev) if self.overlap else None
+        self._plan = None
+        self._plan_host = None            # id of the pinned host batch the look-ahead plan was computed for
+        self._staged = [None, None]       # (id of the pinned host batch uploaded into the set, upload event)
         self.d_cloud, self.d_pcld, self.d_labels, self.d_ctr_of, self.d_kp_of = (
             self._sets[0][k] for k in ("cld_rgb_nrm", "pcld", "labels", "ctr_of", "kp_of"))
         # pinned result buffers, one pair per staging set: call i+1 must not overwrite what call i returned
@@ -84,19 +94,43 @@ class FramePipeline:
         return {k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in batch.items()}
 
     @torch.no_grad()
-    def run_device(self, cld_rgb_nrm, pcld, labels, ctr_of, kp_of):
-        """inputs resident in HBM; returns device views (poses [B,n_cls,3,4], present [B,n_cls])."""
+    def run_device(self, cld_rgb_nrm, pcld, labels, ctr_of, kp_of, next_cloud=None):
+        """inputs resident in HBM; returns device views (poses [B,n_cls,3,4], present [B,n_cls]).
+        next_cloud: the cld_rgb_nrm tensor of the batch the NEXT call will process (or (tensor, event that
+        signals its upload)): its geometry plan is computed on a side stream during this call."""
         cur = torch.cuda.current_stream(self.dev)
-        if self.overlap:
-            ready = torch.cuda.Event()
-            ready.record(cur)
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        if self._pose_stream is not None:
             self._pose_stream.wait_event(ready)          # inputs (and the previous reader of the outputs) are done
             with torch.cuda.stream(self._pose_stream):
                 poses, present, _, _ = self.solver.solve(pcld, labels, ctr_of, kp_of)   # hot path B
                 solved = torch.cuda.Event()
                 solved.record(self._pose_stream)
         if self.fused is not None:
-            self.features = self.fused(cld_rgb_nrm)                       # hot path A: [B,128,N]
+            plan, self._plan = self._plan, None
+            if plan is not None and plan.key != (cld_rgb_nrm.data_ptr(), tuple(cld_rgb_nrm.shape)):
+                plan = None                                               # the look-ahead was for another batch
+            if plan is None:
+                plan = self.fused.geometry(cld_rgb_nrm)                   # no look-ahead: geometry first, whole GPU
+            else:
+                cur.wait_event(plan.done)
+                for t in plan.tensors():
+                    t.record_stream(cur)                                  # allocated on the geometry stream
+            reserve = 0
+            if next_cloud is not None and self.overlap:
+                nc, uploaded = next_cloud if isinstance(next_cloud, tuple) else (next_cloud, None)
+                g = self._geo_stream
+                g.wait_event(ready)
+                if uploaded is not None:
+                    g.wait_event(uploaded)
+                with torch.cuda.stream(g):
+                    nplan = self.fused.sampling(nc, fps_chunk=self.fps_chunk)
+                    nplan.done = torch.cuda.Event()
+                    nplan.done.record(g)
+                self._plan = nplan
+                reserve = min(self.fps_chunk, nc.size(0))
+            self.features = self.fused.features(cld_rgb_nrm, plan, reserve_sms=reserve)   # hot path A: [B,128,N]
         else:
             prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
             torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = self.allow_tf32
@@ -104,24 +138,15 @@ class FramePipeline:
                 self.features = self.model(cld_rgb_nrm)
             finally:
                 torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = prev
-        if self.overlap:
+        if self._pose_stream is not None:
             cur.wait_event(solved)
         else:
             poses, present, _, _ = self.solver.solve(pcld, labels, ctr_of, kp_of)   # hot path B
         return poses, present
 
-    @torch.no_grad()
-    def run_host(self, hb: Dict[str, torch.Tensor]):
-        """hb: pinned host tensors (pin_batch).  H2D copies, both hot paths, D2H of the poses; the
-        caller synchronises the stream before reading the returned pinned host tensors.  The copies
-        go through a second stream into one of two staging sets: back-to-back calls overlap the
-        upload of call i with the kernels of call i-1.  The returned pinned buffers alternate too: the
-        result of call i stays valid until call i+2."""
-        b = hb["pcld"].shape[0]
-        turn = self._turn
-        self._turn ^= 1
+    def _upload(self, hb: Dict[str, torch.Tensor], turn: int):
         st = self._sets[turn]
-        cur = torch.cuda.current_stream(self.dev)
+        b = hb["pcld"].shape[0]
         with torch.cuda.stream(self._copy_stream):
             if self._set_free[turn] is not None:
                 self._copy_stream.wait_event(self._set_free[turn])
@@ -129,9 +154,40 @@ class FramePipeline:
                 st[key][:b].copy_(hb[key], non_blocking=True)
             uploaded = torch.cuda.Event()
             uploaded.record(self._copy_stream)
+        self._staged[turn] = (id(hb), uploaded)
+        return uploaded
+
+    @torch.no_grad()
+    def run_host(self, hb: Dict[str, torch.Tensor], next_hb: Optional[Dict[str, torch.Tensor]] = None):
+        """hb: pinned host tensors (pin_batch).  H2D copies, both hot paths, D2H of the poses; the
+        caller synchronises the stream before reading the returned pinned host tensors.  The copies
+        go through a second stream into one of two staging sets: back-to-back calls overlap the
+        upload of call i with the kernels of call i-1.  The returned pinned buffers alternate too: the
+        result of call i stays valid until call i+2.
+        next_hb: the batch the NEXT call will process: it is uploaded now (into the other staging set) and its
+        geometry plan is computed under this call's shared MLPs (see run_device)."""
+        b = hb["pcld"].shape[0]
+        turn = self._turn
+        self._turn ^= 1
+        st = self._sets[turn]
+        cur = torch.cuda.current_stream(self.dev)
+        tag = self._staged[turn]
+        if self._plan is not None and self._plan_host != id(hb):
+            # the look-ahead named another batch: drop its plan (the staging buffer it was computed from has this
+            # call's address) and let the sampler finish reading that buffer before it is overwritten
+            self._copy_stream.wait_event(self._plan.done)
+            self._plan = None
+        self._plan_host = None
+        uploaded = tag[1] if (tag is not None and tag[0] == id(hb)) else self._upload(hb, turn)
+        self._staged[turn] = None
         cur.wait_event(uploaded)
+        next_cloud = None
+        if next_hb is not None and self.overlap and self.fused is not None:
+            up2 = self._upload(next_hb, turn ^ 1)
+            next_cloud = (self._sets[turn ^ 1]["cld_rgb_nrm"][:next_hb["pcld"].shape[0]], up2)
+            self._plan_host = id(next_hb)
         poses, present = self.run_device(st["cld_rgb_nrm"][:b], st["pcld"][:b], st["labels"][:b],
-                                         st["ctr_of"][:b], st["kp_of"][:b])
+                                         st["ctr_of"][:b], st["kp_of"][:b], next_cloud=next_cloud)
         done = torch.cuda.Event()
         done.record(cur)
         self._set_free[turn] = done

@@ -52,3 +52,32 @@ def test_frame_pipeline_recovers_synthetic_poses(cuda_dev, shape, batch, engine)
             # votes carry 5 mm noise: the recovered translation must land within a few mm
             assert np.linalg.norm(poses[bi, int(c)][:, 3] - gt[:, 3]) < 0.01
             assert np.linalg.norm(poses[bi, int(c)][:, :3] - gt[:, :3]) < 0.2
+
+
+def test_lookahead_pipeline_equals_serial_pipeline(cuda_dev):
+    """the geometry plan of batch i+1 computed on a side stream under the MLPs of batch i (run_device(next_cloud=),
+    run_host(hb, next_hb)) must not change a single bit of the features or the poses"""
+    n, b = 4096, 3
+    batches = [synth.stack(synth.make_batch("ycb", b, n_points=n, config_id=20 + j)) for j in range(4)]
+    serial = FramePipeline("ycb", b, n_points=n, device=cuda_dev, overlap=False)
+    ahead = FramePipeline("ycb", b, n_points=n, device=cuda_dev, overlap=True, fps_chunk=2)
+    dev = [{k: torch.from_numpy(np.ascontiguousarray(v)).to(cuda_dev) for k, v in hb.items()} for hb in batches]
+    want = []
+    for d in dev:
+        p, pr = serial.run_device(d["cld_rgb_nrm"], d["pcld"], d["labels"], d["ctr_of"], d["kp_of"])
+        want.append((serial.features.clone(), p.clone(), pr.clone()))
+    for j, d in enumerate(dev):
+        nxt = dev[j + 1]["cld_rgb_nrm"] if j + 1 < len(dev) else None
+        p, pr = ahead.run_device(d["cld_rgb_nrm"], d["pcld"], d["labels"], d["ctr_of"], d["kp_of"], next_cloud=nxt)
+        torch.cuda.synchronize()
+        assert torch.equal(ahead.features, want[j][0]), j
+        assert torch.equal(p, want[j][1]) and torch.equal(pr, want[j][2]), j
+    # host path: uploads of the next batch + plan under the current one; a wrong prediction falls back cleanly
+    pinned = [FramePipeline.pin_batch(hb) for hb in batches]
+    order = [0, 1, 2, 3, 1]
+    for j, bi in enumerate(order):
+        nxt = pinned[order[j + 1]] if j + 1 < len(order) and j != 2 else (pinned[0] if j == 2 else None)   # j == 2 mispredicts
+        p, pr = ahead.run_host(pinned[bi], nxt)
+        torch.cuda.synchronize()
+        assert torch.equal(ahead.features, want[bi][0]), (j, bi)
+        assert torch.equal(p.to(cuda_dev), want[bi][1]) and torch.equal(pr.to(cuda_dev), want[bi][2]), (j, bi)

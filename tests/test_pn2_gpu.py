@@ -98,6 +98,10 @@ def test_group_and_gather_bit_exact(cuda_dev, clouds):
         fidx = pn2.furthest_point_sampling(xyz, m)
         g2 = _ext.gather_points(t(feats, cuda_dev), t(fidx, cuda_dev)).cpu().numpy()
         assert np.array_equal(g2, pn2.gather_points(feats, fidx))
+        # point-major centre gather == gather_operation(xyz^T, idx)^T (pointnet2_modules.py:47-53)
+        nx = _ext.gather_xyz(t(xyz, cuda_dev), t(fidx, cuda_dev)).cpu().numpy()
+        want = pn2.gather_points(np.ascontiguousarray(xyz.transpose(0, 2, 1)), fidx).transpose(0, 2, 1)
+        assert np.array_equal(nx, want)
 
 
 def test_query_and_group_fused_bit_exact(cuda_dev, clouds):
