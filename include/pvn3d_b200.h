@@ -152,10 +152,11 @@ int pvn3d_three_nn_interpolate(const float *unknown, const float *known, const f
  *   out  point-major rows of length ldo (ldo, col0 multiples of 4); pool in {0, 8, 16, 32}
  * Arithmetic: TF32 operands (round-to-nearest), fp32 accumulation in TMEM.
  * flags: PVN3D_MLP_RELU       apply ReLU (flags = 1 / 0 is the plain relu switch)
- *        PVN3D_MLP_ROUND_OUT  store the activations already rounded to TF32 (ignored with pool)
- *        PVN3D_MLP_A_TF32     (mlp_dense) `a` was produced with ROUND_OUT and is 16-byte aligned with
- *                             lda % 4 == 0: it is copied global -> shared asynchronously, without the
- *                             rounding pass (an unrounded `a` would be TRUNCATED by the tensor core)
+ *        PVN3D_MLP_ROUND_OUT  store the activations (pooled or not) already rounded to TF32
+ *        PVN3D_MLP_A_TF32     (mlp_dense) `a` / (mlp_sa_first) `feat_pm` was produced with ROUND_OUT and is
+ *                             16-byte aligned with a leading dimension % 4 == 0: its rows are copied global ->
+ *                             shared asynchronously, without the rounding pass (unrounded values would be
+ *                             TRUNCATED by the tensor core)
  * ---------------------------------------------------------------------------------------- */
 #define PVN3D_MLP_RELU 1
 #define PVN3D_MLP_ROUND_OUT 2

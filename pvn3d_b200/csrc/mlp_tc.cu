@@ -492,7 +492,11 @@ __global__ void __launch_bounds__(kMlpThreads, OCC) mlp_layer_kernel(const __gri
       vec_ok = a.c_feat > 0 && (a.ldf % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.feat) & 15u) == 0);
     if (PRO == PRO_FP_INTERP)
       vec_ok = (a.c2 % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.known_feat) & 15u) == 0);
-    const bool a_async = PRO == PRO_DENSE && a.a_tf32 && vec_ok;
+    // pre-rounded rows are copied global -> shared asynchronously: DENSE activations of a ROUND_OUT layer, and
+    // the descriptor columns of SA_GATHER rows when the level table was stored rounded (PVN3D_MLP_A_TF32);
+    // the xyz / padding chunk of a gathered row and everything else is staged through registers
+    const bool a_async = (PRO == PRO_DENSE || PRO == PRO_SA_GATHER) && a.a_tf32 && vec_ok;
+    const int async_cols = PRO == PRO_DENSE ? a.k_pad : (a.c_feat / 32) * 32;   // chunks [0, async_cols) are asynchronous
     int pend0 = 0, pend1 = 0, npend = 0;  // stages whose copies are committed but not yet published
     long long it_base = 0;  // number of K chunks staged before this tile (same in every role)
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, it_base += kc_total) {
@@ -533,20 +537,24 @@ __global__ void __launch_bounds__(kMlpThreads, OCC) mlp_layer_kernel(const __gri
             cp_async16(sb + sw128_off(n, c), a.w + static_cast<size_t>(n0 + n) * a.k_pad + kc * 32 + c * 4);
           }
         }
-        if (a_async) {
+        if (a_async && kc * 32 < async_cols) {
           const int k = kc * 32 + 4 * sub;
+          const int valid = PRO == PRO_DENSE ? a.a_cols : a.c_feat;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            cp_async16(sa + sw128_off(r_first + 4 * j, sub), rs.row[j] + (k < a.a_cols ? k : 0),
-                       (((rs.live >> j) & 1u) && k < a.a_cols) ? 16u : 0u);
+            cp_async16(sa + sw128_off(r_first + 4 * j, sub), rs.row[j] + (k < valid ? k : 0),
+                       (((rs.live >> j) & 1u) && k < valid) ? 16u : 0u);
           cp_async_commit();
           if (npend == 0) pend0 = s; else pend1 = s;
           ++npend;
         } else {
           cp_async_commit();
           stage_a_chunk<PRO>(a, rs, p_first, r_first, sub, kc * 32, sa, vec_ok);
-          cp_async_wait<0>();        // the weights of this chunk (issued before the A gather) have landed
+          cp_async_wait<0>();        // the weights of this chunk and every asynchronous chunk still pending have landed
           fence_proxy_async_smem();  // generic-proxy stores / copies -> visible to the tensor-core proxy
+          if (npend >= 1) mbar_arrive(&ctl.full[pend0]);
+          if (npend == 2) mbar_arrive(&ctl.full[pend1]);
+          npend = 0;
           mbar_arrive(&ctl.full[s]);
         }
       }
@@ -631,6 +639,7 @@ __global__ void __launch_bounds__(kMlpThreads, OCC) mlp_layer_kernel(const __gri
             if (col < cw && p0 + warp * 32 < a.rows) {
               float r = v[0] + __ldg(a.bias + n0 + c0 + col);
               if (a.relu) r = fmaxf(r, 0.f);
+              if (a.round_out) r = to_tf32(r);
               a.out[grow0 * a.ldo + a.col0 + n0 + c0 + col] = r;
             }
           } else if (a.pool == 16) {
@@ -641,6 +650,7 @@ __global__ void __launch_bounds__(kMlpThreads, OCC) mlp_layer_kernel(const __gri
               r.x = v[0] + __ldg(a.bias + n0 + c0 + col);
               r.y = v[1] + __ldg(a.bias + n0 + c0 + col + 1);
               if (a.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); }
+              if (a.round_out) { r.x = to_tf32(r.x); r.y = to_tf32(r.y); }
               *reinterpret_cast<float2 *>(a.out + (grow0 + g) * a.ldo + a.col0 + n0 + c0 + col) = r;
             }
           } else {  // pool == 8
@@ -654,6 +664,9 @@ __global__ void __launch_bounds__(kMlpThreads, OCC) mlp_layer_kernel(const __gri
               r.w = v[3] + __ldg(a.bias + n0 + c0 + col + 3);
               if (a.relu) {
                 r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
+              }
+              if (a.round_out) {
+                r.x = to_tf32(r.x); r.y = to_tf32(r.y); r.z = to_tf32(r.z); r.w = to_tf32(r.w);
               }
               *reinterpret_cast<float4 *>(a.out + (grow0 + g) * a.ldo + a.col0 + n0 + c0 + col) = r;
             }
@@ -725,7 +738,7 @@ int launch_mlp(MlpArgs &a, cudaStream_t st) {
   static const int occ_env = [] { const char *e = getenv("PVN3D_MLP_OCC"); return e ? atoi(e) : 0; }();
   const size_t budget2 = (92 * 1024);   // ring of one of two co-resident CTAs (+17 KB control and staging each)
   // asynchronous producers (pre-rounded dense activations) keep two chunks in flight: >= 3 stages
-  const size_t min_stages = (PRO == PRO_DENSE && a.a_tf32) ? 3 : 2;
+  const size_t min_stages = ((PRO == PRO_DENSE || PRO == PRO_SA_GATHER) && a.a_tf32) ? 3 : 2;
   bool occ2 = a.tmem_cols <= 128 && min_stages * stage_bytes <= budget2 && tiles >= 4ll * sms;
   if (occ_env == 1) occ2 = false;
   int stages = static_cast<int>((occ2 ? budget2 : size_t(208 * 1024)) / stage_bytes);
@@ -1291,7 +1304,7 @@ extern "C" int pvn3d_mlp_dense(const float *a, int lda, int a_cols, long long ro
   m.w = w; m.bias = bias; m.rows = rows; m.k_pad = k_pad; m.n_pad = n_pad;
   m.a = a; m.lda = lda; m.a_cols = a_cols;
   m.out = out; m.ldo = ldo; m.col0 = col0;
-  m.relu = flags & PVN3D_MLP_RELU; m.round_out = (flags & PVN3D_MLP_ROUND_OUT) && !pool;
+  m.relu = flags & PVN3D_MLP_RELU; m.round_out = (flags & PVN3D_MLP_ROUND_OUT) ? 1 : 0;
   m.a_tf32 = (flags & PVN3D_MLP_A_TF32) ? 1 : 0;
   m.reserve_sms = (flags >> 8) & 0xff;
   return dispatch(m, PRO_DENSE, pool, as_stream(stream));
@@ -1315,6 +1328,7 @@ extern "C" int pvn3d_mlp_sa_first(const float *xyz, const float *new_xyz, const 
   a.n = n; a.m = m; a.ns = ns;
   a.out = out; a.ldo = ldo; a.col0 = col0;
   a.relu = flags & PVN3D_MLP_RELU; a.round_out = (flags & PVN3D_MLP_ROUND_OUT) ? 1 : 0;
+  a.a_tf32 = (flags & PVN3D_MLP_A_TF32) ? 1 : 0;   // feat_pm rows are TF32-rounded: asynchronous copies
   a.reserve_sms = (flags >> 8) & 0xff;
   return dispatch(a, PRO_SA_GATHER, pool, as_stream(stream));
 }

@@ -93,7 +93,7 @@ def mlp_dense(a2d: torch.Tensor, layer: PackedLayer, relu=True, pool=0, out=None
 
 
 def mlp_sa_first(xyz, new_xyz, feat_pm, ldf, c_feat, idx, layer: PackedLayer, relu=True, pool=0, out=None, col0=0,
-                 round_out=False, reserve=0):
+                 round_out=False, reserve=0, feat_tf32=False):
     lib = _lib.load()
     b, n = xyz.shape[0], xyz.shape[1]
     m, ns = idx.shape[1], idx.shape[2]
@@ -102,7 +102,7 @@ def mlp_sa_first(xyz, new_xyz, feat_pm, ldf, c_feat, idx, layer: PackedLayer, re
         out = torch.empty((rows // pool if pool else rows, layer.n_pad), dtype=torch.float32, device=xyz.device)
     with torch.cuda.device(xyz.device):
         rc = lib.pvn3d_mlp_sa_first(ptr(xyz), ptr(new_xyz), feat_pm, ldf, c_feat, ptr(idx), b, n, m, ns, ptr(layer.w),
-                                    ptr(layer.bias), layer.k_pad, layer.n_pad, _flags(relu, round_out, reserve=reserve), pool, ptr(out),
+                                    ptr(layer.bias), layer.k_pad, layer.n_pad, _flags(relu, round_out, feat_tf32, reserve), pool, ptr(out),
                                     out.size(-1), col0, _stream(xyz.device))
     check(rc, "pvn3d_mlp_sa_first")
     return out
@@ -240,6 +240,9 @@ class FusedPointnet2MSG:
                 prev_pad = pl.n_pad
                 layers.append(pl)
             self.fp.append(layers)
+        #: store the level tables of SA1-3 TF32-rounded so that the next level gathers them with cp.async
+        #: (identical features: every reader of those tables rounds on staging; PVN3D_MLP_ROUND_TABLES=0 disables)
+        self.round_tables = (not self.chain) and os.environ.get("PVN3D_MLP_ROUND_TABLES", "1") != "0"
         self.sa_chain = [[LayerChain(layers) for layers in scales] for scales in self.sa] if self.chain else None
         self.fp_chain = [LayerChain(layers) for layers in self.fp] if self.chain else None
         self._marks = None
@@ -347,11 +350,16 @@ class FusedPointnet2MSG:
                                  out=out_l.view(b * npoint, -1), col0=col, reserve=rs)
                     col += layers[-1].n
                     continue
-                # intermediates are stored TF32-rounded (what the next layer's operand is anyway)
-                h = mlp_sa_first(x, new_xyz, fptr, ldf, c_feat, idx, layers[0], round_out=True, reserve=rs)
+                # intermediates are stored TF32-rounded (what the next layer's operand is anyway); so are the
+                # level tables of SA1-3, whose only readers round them anyway (SA gather producers, FP skip
+                # columns): their rows then go global -> shared by cp.async (SA4's table feeds the fp32
+                # interpolation of FP4 and stays unrounded)
+                h = mlp_sa_first(x, new_xyz, fptr, ldf, c_feat, idx, layers[0], round_out=True, reserve=rs,
+                                 feat_tf32=self.round_tables and li >= 1)
                 for mid in layers[1:-1]:
                     h = mlp_dense(h, mid, round_out=True, a_tf32=True, reserve=rs)
-                mlp_dense(h, layers[-1], pool=ns, out=out_l.view(b * npoint, -1), col0=col, a_tf32=True, reserve=rs)
+                mlp_dense(h, layers[-1], pool=ns, out=out_l.view(b * npoint, -1), col0=col, a_tf32=True, reserve=rs,
+                          round_out=self.round_tables and li < 3)
                 col += layers[-1].n
             self._m("mlp")
             feats.append((out_l.data_ptr(), out_l.size(-1), out_l.size(-1)))

@@ -69,7 +69,9 @@ class FramePipeline:
         #: batch.  The sampling kernels are launched `fps_chunk` frames at a time and the persistent MLP kernels
         #: leave that many SMs free (PVN3D_MLP_RESERVE_SMS), so neither side ever waits for an SM.
         self.fps_chunk = max(1, min(int(fps_chunk), self.b))
-        self._geo_stream = torch.cuda.Stream(self.dev) if self.overlap else None
+        # high priority: a sampling CTA needs a whole SM (512 threads, ~56 K registers, 147 KB shared memory); when
+        # an SM drains, it must win it before the thousands of small CTAs of hot path B refill it
+        self._geo_stream = torch.cuda.Stream(self.dev, priority=-1) if self.overlap else None
         self._plan = None
         self._plan_host = None            # id of the pinned host batch the look-ahead plan was computed for
         self._staged = [None, None]       # (id of the pinned host batch uploaded into the set, upload event)

@@ -232,3 +232,19 @@ def test_chain_engine_equals_layer_engine_and_is_deterministic(cuda_dev):
     assert torch.equal(y0, y_layer), float((y0 - y_layer).abs().max())
     for i in range(200):
         assert torch.equal(eng(x), y0), f"run {i} differs"
+
+
+def test_rounded_level_tables_do_not_change_the_features(cuda_dev):
+    """SA1-3 level tables stored TF32-rounded (so that the next level gathers them with cp.async) vs stored in
+    fp32 and rounded while staging: identical features, bit for bit"""
+    from pvn3d_b200 import synth
+
+    model = testing.seeded_pointnet2msg(0, 1)
+    frames = synth.make_batch("linemod", 2, n_points=12288, config_id=14)
+    x = torch.from_numpy(np.stack([f.cld_rgb_nrm for f in frames])).to(cuda_dev)
+    eng = mlp.FusedPointnet2MSG(model, cuda_dev, chain=False)
+    assert eng.round_tables
+    y_async = eng(x).clone()
+    eng.round_tables = False
+    y_sync = eng(x)
+    assert torch.equal(y_async, y_sync), float((y_async - y_sync).abs().max())
