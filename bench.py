@@ -312,13 +312,18 @@ class Runner:
         return pdist.max_over_ranks(ms, self.dev), (lib.pvn3d_launch_count() - l0 if lib is not None else 0)
 
     def measure(self, steps, warmup, lib, e2e=True, clocks=True):
-        for i in range(warmup):
+        # W untimed steps of exactly the loop that is timed next (indices -W..-1, so that the look-ahead of the
+        # last warm-up step names the first timed batch), then K timed steps; first the device-resident loop,
+        # then the same for the host loop
+        for i in range(-warmup, 0):
             self.step_device(i)
-            if e2e:
-                self.step_host(i)
         sampler = ClockSampler(self.dev.index or 0).start() if (clocks and self.rank == 0) else None
         ms_dev, launches = self.timed(self.step_device, steps, lib)
-        ms_e2e = self.timed(self.step_host, steps)[0] if e2e else None
+        ms_e2e = None
+        if e2e:
+            for i in range(-warmup, 0):
+                self.step_host(i)
+            ms_e2e = self.timed(self.step_host, steps)[0]
         ck = sampler.stop() if sampler is not None else None
         frames = self.B * self.world * steps
         out = {"value": frames / (ms_dev * 1e-3), "unit": "frames/s", "ms_per_step": ms_dev / steps,
@@ -427,7 +432,10 @@ def roofline_query_group(torch, _ext, dev, B, cloud, peak, peak_kind):
                       "of a level per call: 4 calls of one batch)",
             "on_timed_step": False, "where": "module-graph API (QueryAndGroup.forward); the fused step never writes the grouped tensor",
             "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_kind": peak_kind,
-            "traffic": None, "algorithmic_MB_per_batch": total_bytes / 1e6, "us_per_batch": total_ms * 1e3, "per_launch": per}
+            # dram bytes of the same four calls (8 kernels) from one `ncu --set full` capture (profiles/ncu_qgsplit_r01u.md,
+            # kernels unchanged since): below the algorithmic bytes -- the descriptor tables are L2 hits
+            "traffic": 2005.4 if B == 32 else None, "traffic_unit": "MB per batch (ncu, profiles/ncu_qgsplit_r01u.md)",
+            "algorithmic_MB_per_batch": total_bytes / 1e6, "us_per_batch": total_ms * 1e3, "per_launch": per}
 
 
 def stock_gpu_baseline(torch, runner, dev):
@@ -545,7 +553,11 @@ def b200_arm(args, json_out):
             mlp_roof = {"kernel": "mlp_layer_kernel (all shared-MLP launches of one batch: SA 8 scales x 3 layers, FP 4 x 2)",
                         "on_timed_step": True, "bound": "hbm", "achieved": MLP_IO_BYTES * B / t_mlp / 1e6, "peak": peak,
                         "unit": "GB/s", "frac": MLP_IO_BYTES * B / t_mlp / 1e6 / peak, "peak_kind": peak_kind,
-                        "traffic": None, "ms_per_batch": t_mlp, "algorithmic_MB_per_batch": MLP_IO_BYTES * B / 1e6,
+                        # dram__bytes_read.sum + dram__bytes_write.sum over the 32 launches of one batch, `ncu --set full`
+                        # (profiles/ncu_mlp_r02.md): 2.1x the algorithmic bytes -- the inter-layer activations
+                        "traffic": 6863.8 if (B == 32 and cfg["shape"] == "linemod" and not run.pipe.fused.chain) else None,
+                        "traffic_unit": "MB per batch (ncu, profiles/ncu_mlp_r02.md)",
+                        "ms_per_batch": t_mlp, "algorithmic_MB_per_batch": MLP_IO_BYTES * B / 1e6,
                         "useful_TFLOPs": MLP_FLOPS * B / t_mlp / 1e9,
                         "note": "algorithmic bytes = SURVEY 8d MLP stage I/O with every SharedMLP(+max-pool) fused (100.2 MB/frame); "
                                 "inter-layer activations that still round-trip HBM are NOT counted as useful"}
@@ -676,7 +688,7 @@ def main():
     sys.stdout.flush()
     json_out = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
-    args.warmup = max(args.warmup, 3 if args.impl == "b200" else 0)
+    args.warmup = max(args.warmup, 5 if args.impl == "b200" else 0)   # the first steps of a loop grow the allocator pools
     if args.impl == "reference":
         rank = int(os.environ.get("RANK", "0"))
         return reference_arm(args, json_out, rank)

@@ -203,22 +203,39 @@ __device__ __forceinline__ void best3_push(Best3 &b, float d, int k) {
 
 // scans known[0..m) of cloud b for the calling thread's query point (ux,uy,uz); all threads of the
 // CTA must call it (barriers inside).
+// The tile holds NEGATED known points as pairs, s_known[2p] = (-x0,-x1,-y0,-y1), s_known[2p+1] = (-z0,-z1,.,.):
+// u - q = u + (-q) exactly, so the distance of the query to two known points is three FADD2 + FMUL2 + two
+// FFMA2 on the packed fp32 pipe -- per lane the same IEEE operations in the same order as ref_sqdist
+// (fma(dz,dz, fma(dx,dx, dy*dy))), pushed in index order: results stay bit-exact.  An odd tail is a point
+// at infinity (d2 = inf never beats a finite or an initial inf candidate).
 __device__ __forceinline__ void three_nn_scan(const float *__restrict__ known_cloud, int m,
                                               float4 *s_known, float ux, float uy, float uz,
                                               Best3 &best) {
   best3_init(best);
+  const float2 ux2 = make_float2(ux, ux), uy2 = make_float2(uy, uy), uz2 = make_float2(uz, uz);
+  const float ninf = -__int_as_float(0x7f800000);
   for (int base = 0; base < m; base += kNnTile) {
     const int count = min(kNnTile, m - base);
+    const int npairs = (count + 1) >> 1;
     __syncthreads();
-    for (int i = threadIdx.x; i < count; i += blockDim.x) {
-      const float *p = known_cloud + static_cast<size_t>(base + i) * 3;
-      s_known[i] = make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
+    for (int i = threadIdx.x; i < npairs; i += blockDim.x) {
+      const float *p = known_cloud + static_cast<size_t>(base + 2 * i) * 3;
+      const bool two = 2 * i + 1 < count;
+      const float x0 = __ldg(p), y0 = __ldg(p + 1), z0 = __ldg(p + 2);
+      const float x1 = two ? __ldg(p + 3) : -ninf, y1 = two ? __ldg(p + 4) : -ninf, z1 = two ? __ldg(p + 5) : -ninf;
+      s_known[2 * i] = make_float4(-x0, -x1, -y0, -y1);
+      s_known[2 * i + 1] = make_float4(-z0, -z1, 0.f, 0.f);
     }
     __syncthreads();
 #pragma unroll 4
-    for (int k = 0; k < count; ++k) {
-      const float4 q = s_known[k];
-      best3_push(best, ref_sqdist(ux - q.x, uy - q.y, uz - q.z), base + k);
+    for (int k = 0; k < npairs; ++k) {
+      const float4 a = s_known[2 * k], c = s_known[2 * k + 1];
+      const float2 dx = __fadd2_rn(make_float2(a.x, a.y), ux2);
+      const float2 dy = __fadd2_rn(make_float2(a.z, a.w), uy2);
+      const float2 dz = __fadd2_rn(make_float2(c.x, c.y), uz2);
+      const float2 d = __ffma2_rn(dz, dz, __ffma2_rn(dx, dx, __fmul2_rn(dy, dy)));
+      best3_push(best, d.x, base + 2 * k);
+      best3_push(best, d.y, base + 2 * k + 1);
     }
   }
 }

@@ -116,9 +116,12 @@ class FramePipeline:
             if plan is None:
                 plan = self.fused.geometry(cld_rgb_nrm)                   # no look-ahead: geometry first, whole GPU
             else:
+                # The plan's tensors were allocated on the sampling stream and are read here on `cur`.  No
+                # record_stream() is needed (and its deferred frees made the caching allocator call cudaMalloc
+                # every few steps): the plan is dropped when this call returns, its blocks go back to the
+                # sampling stream's pool, and the next allocation from that pool is the sampling of call i+1,
+                # which waits for `ready` of call i+1 -- recorded on `cur` after everything enqueued here.
                 cur.wait_event(plan.done)
-                for t in plan.tensors():
-                    t.record_stream(cur)                                  # allocated on the geometry stream
             reserve = 0
             if next_cloud is not None and self.overlap:
                 nc, uploaded = next_cloud if isinstance(next_cloud, tuple) else (next_cloud, None)

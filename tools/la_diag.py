@@ -26,3 +26,20 @@ for la in (True, False):
         ts = [ev[i].elapsed_time(ev[i + 1]) for i in range(n)]
         print("lookahead" if la else "serial   ", "rep", rep, "total/step %.3f" % (ev[0].elapsed_time(ev[n]) / n),
               "median %.3f min %.3f max %.3f" % (statistics.median(ts), min(ts), max(ts)), [round(t, 1) for t in ts[:16]])
+
+# host loop (e2e): pinned host batches, uploads inside the loop
+pinned = [FramePipeline.pin_batch({k: np.roll(v, 8 * r, axis=0).copy() for k, v in host.items()}) for r in range(4)]
+for la in (True, False):
+    pipe = FramePipeline("linemod", B, device=dev, lm_obj_id=1)
+    n = 40
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+    for rep in range(3):
+        torch.cuda.synchronize()
+        for i in range(n):
+            ev[i].record()
+            pipe.run_host(pinned[i % 4], pinned[(i + 1) % 4] if la else None)
+        ev[n].record()
+        torch.cuda.synchronize()
+        ts = [ev[i].elapsed_time(ev[i + 1]) for i in range(n)]
+        print("host lookahead" if la else "host serial   ", "rep", rep, "total/step %.3f" % (ev[0].elapsed_time(ev[n]) / n),
+              "median %.3f min %.3f max %.3f" % (statistics.median(ts), min(ts), max(ts)), [round(t, 1) for t in ts[:24]])

@@ -46,7 +46,7 @@ def launches(tag):
     tot = sum(v for _, v in agg.values())
     with open(os.path.join(OUT, f"launches_{tag}.md"), "w") as f:
         f.write(f"# ncu launch list, tag {tag}: `ncu --metrics gpu__time_duration.sum --clock-control none` over "
-                f"`python bench.py --steps 1 --warmup 3 --no-cpu-baseline`\n\n"
+                f"`python bench.py --steps 1 --warmup 3 --quick --no-overlap`\n\n"
                 f"Per-launch times are cold-cache and serialised: read the SHARES.  {sum(n for n, _ in agg.values())} launches, "
                 f"{tot / 1e3:.1f} ms total.\n\n| kernel | launches | total ms | share |\n|---|---:|---:|---:|\n")
         for k, (n, v) in sorted(agg.items(), key=lambda x: -x[1][1])[:30]:
@@ -61,7 +61,10 @@ def full(tag, name):
     rd = list(csv.reader(out.splitlines()))
     hdr, units, rows = rd[0], rd[1], rd[2:]
     with open(os.path.join(OUT, f"ncu_{name}_{tag}.md"), "w") as f:
+        kn = hdr.index("Kernel Name") if "Kernel Name" in hdr else None
         f.write(f"# ncu --set full, tag {tag}, kernels matching `{name}` ({len(rows)} launches captured)\n\n")
+        if kn is not None:
+            f.write("Launches: " + "; ".join(f"{i}: `{re.sub(r'[(].*', '', r[kn])[-60:]}`" for i, r in enumerate(rows)) + "\n\n")
         f.write("| metric | unit | " + " | ".join(f"launch {i}" for i in range(len(rows))) + " |\n")
         f.write("|---|---|" + "---:|" * len(rows) + "\n")
         for k in KEYS:
@@ -74,7 +77,9 @@ if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
     os.makedirs(OUT, exist_ok=True)
     launches(tag)
-    full(tag, "qg")
-    full(tag, "ms")
-    full(tag, "mlp")
-    print(os.listdir(OUT))
+    for name in ("qg", "ms", "mlp", "msdens", "mswit", "fps", "nn", "ball", "chain"):
+        gz = os.path.join(ROOT, "gpurun_out", f"prof_{name}_{tag}.ncu-rep.gz")
+        if os.path.exists(gz) and not os.path.exists(gz[:-3]):
+            subprocess.run(["gunzip", "-kf", gz])
+        full(tag, name)
+    print(sorted(os.listdir(OUT)))
