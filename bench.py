@@ -242,6 +242,26 @@ def reference_arm(args, json_out, rank):
     return 0
 
 
+def cpu_pose_path_ycb(frame, gpu_ms_per_frame):
+    """north_star: ">= 200x the reference CPU MeanShift wall-clock on 12288-point YCB-shape clouds at 1 GPU".
+    One COMPLETE YCB frame of hot path B on the host cores through the CPU port (oracle/frame_poses_oracle.py =
+    pvn3d_eval_utils.py:37-110 on CPU tensors: centre-cluster filter pass, 5 classes x (1 + 8) fits, Kabsch)."""
+    import torch
+    from oracle import frame_poses_oracle
+    from pvn3d_b200 import fixtures
+
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
+    args = (torch.from_numpy(frame.pcld), torch.from_numpy(frame.labels), torch.from_numpy(frame.ctr_of),
+            torch.from_numpy(frame.kp_of))
+    r = fixtures.ycb_r_lst()
+    t0 = time.perf_counter()
+    frame_poses_oracle.cal_frame_poses(*args, True, 22, True, lambda c: fixtures.get_kps(c), lambda c: fixtures.get_ctr(c), r)
+    sec = time.perf_counter() - t0
+    return {"cpu_s_per_frame": sec, "threads": torch.get_num_threads(), "gpu_ms_per_frame": gpu_ms_per_frame,
+            "speedup": sec * 1e3 / gpu_ms_per_frame, "kind": "port",
+            "sample": "hot path B of ONE complete YCB frame (5 instances, 50 fits) on the CPU port, wall clock"}
+
+
 def workload_name(cfg):
     return f"{cfg['label']}, batch {cfg['batch']}/GPU"
 
@@ -619,6 +639,8 @@ def b200_arm(args, json_out):
             m["certified_fits"] = r2.pipe.solver.certified_fits() if args.ms_mode == "certified" else None
             r2.set_mode("strict")
             m["path_b_ms_per_batch_strict"] = r2.path_b_ms()
+            if world == 1 and not args.no_cpu_baseline:
+                m["cpu_meanshift"] = cpu_pose_path_ycb(r2.frames[0], m["meanshift_ms_per_frame"])
             subs[key] = m
         del r2
         torch.cuda.empty_cache()
