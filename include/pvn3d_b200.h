@@ -208,6 +208,26 @@ int pvn3d_mlp_fp_chain(const float *known_feat_pm, int c2, const int *nn_idx, co
                        const float *skip_pm, int lds, int c1, int b, int n_unknown, int m_known,
                        const pvn3d_mlp_layer_t *layers, int n_layers, int flags, float *out, int ldo,
                        int col0, void *workspace, size_t workspace_bytes, pvn3d_stream_t stream);
+/* FACTORED first layer of an SA scale.  Conv1x1 + BN is linear before its ReLU, and QueryAndGroup's row is
+ * [f_j | x_j - c_i] (pointnet2_utils.py:311-321), so  W1.[f_j | x_j - c_i] + b1 = U_j - V_i  with
+ *   U_j = W1f.f_j + W1x.x_j   once per POINT    (pvn3d_sa_factor_table + pvn3d_mlp_dense without ReLU), and
+ *   V_i = W1x.c_i - b1        once per CENTRE   (pvn3d_sa_centre_term),
+ * instead of one GEMM row per (centre, neighbour) pair: 5-16x fewer rows.  The second layer then takes
+ * relu(U[idx] - V) as its operand (pvn3d_mlp_sa_fact).  The table carries x as hi + lo TF32 parts (columns
+ * [c_feat, c_feat+3) and [c_feat+3, c_feat+6)), to be multiplied by [W1f | W1x | W1x]: the coordinate term is
+ * evaluated to ~2^-21, MORE accurately than rounding the difference x_j - c_i to TF32 as the unfactored producer
+ * (and cuDNN's TF32 path) does.
+ *   pvn3d_sa_factor_table: xyz [rows,3], feat_pm [rows, ldf] (c_feat columns) -> out [rows, k_pad] TF32-rounded
+ *   pvn3d_sa_centre_term : centres [rows,3], wx [n_pad,3] (TF32-rounded), bias [n_pad] -> out [rows, n_pad]
+ *   pvn3d_mlp_sa_fact    : u [B*n, ldu], v [B*m, ldu] (c_valid columns), idx [B,m,ns] -> layer (w, bias) as
+ *                          pvn3d_mlp_dense: out rows = B*m*ns (or B*m with pool = ns) */
+int pvn3d_sa_factor_table(const float *xyz, const float *feat_pm, int ldf, int c_feat, long long rows, int k_pad,
+                          float *out, pvn3d_stream_t stream);
+int pvn3d_sa_centre_term(const float *centres, const float *wx, const float *bias, long long rows, int n_pad,
+                         float *out, pvn3d_stream_t stream);
+int pvn3d_mlp_sa_fact(const float *u, const float *v, int ldu, int c_valid, const int *idx, int b, int n, int m,
+                      int ns, const float *w, const float *bias, int k_pad, int n_pad, int flags, int pool,
+                      float *out, int ldo, int col0, pvn3d_stream_t stream);
 /* weight[p,0:3] = (1/(sqrt(dist2)+1e-8)) / sum  (pointnet2_modules.py:184-186), fp32 IEEE ops */
 int pvn3d_three_nn_weights(const float *dist2, long long rows, float *weight, pvn3d_stream_t stream);
 

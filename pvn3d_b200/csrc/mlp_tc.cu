@@ -41,7 +41,7 @@ constexpr int kMlpProWarps = 8;  // warps 4-11: two producer groups of 128 threa
 constexpr int kMlpThreads = (kMlpEpiWarps + kMlpProWarps + 1) * 32;  // warp 12: TMEM owner + MMA issuer
 constexpr int kMlpMaxStages = 6;
 
-enum : int { PRO_DENSE = 0, PRO_SA_GATHER = 1, PRO_FP_INTERP = 2 };
+enum : int { PRO_DENSE = 0, PRO_SA_GATHER = 1, PRO_FP_INTERP = 2, PRO_SA_FACT = 3 };
 enum : int { EPI_STORE = 0, EPI_MAXPOOL = 1 };
 
 struct MlpArgs {
@@ -222,8 +222,9 @@ struct RowState {
 template <int PRO>
 __device__ __forceinline__ void rows_setup(const MlpArgs &a, long long p_first, RowState &s) {
   s.live = 0u;
-  const unsigned per_b = PRO == PRO_SA_GATHER ? static_cast<unsigned>(a.m) * static_cast<unsigned>(a.ns)
-                                              : static_cast<unsigned>(a.n_unknown);
+  const unsigned per_b = (PRO == PRO_SA_GATHER || PRO == PRO_SA_FACT)
+                             ? static_cast<unsigned>(a.m) * static_cast<unsigned>(a.ns)
+                             : static_cast<unsigned>(a.n_unknown);
   unsigned b0 = 0, rem0 = 0;
   if (PRO != PRO_DENSE) {
     const long long pf = p_first < a.rows ? p_first : 0;
@@ -247,7 +248,7 @@ __device__ __forceinline__ void rows_setup(const MlpArgs &a, long long p_first, 
     }
     if (PRO == PRO_DENSE) {
       s.row[j] = a.a + pc * a.lda;
-    } else if (PRO == PRO_SA_GATHER) {
+    } else if (PRO == PRO_SA_GATHER || PRO == PRO_SA_FACT) {
       const int q = __ldg(a.idx + pc);
       s.qrow[j] = static_cast<int>(b) * a.n + q;
       s.crow[j] = static_cast<int>(b) * a.m + static_cast<int>(rem / static_cast<unsigned>(a.ns));
@@ -274,6 +275,35 @@ __device__ __forceinline__ void stage_a_chunk(const MlpArgs &a, const RowState &
                                               int r_first, int sub, int k0, uint32_t sa, bool vec_ok) {
   const int k = k0 + 4 * sub;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (PRO == PRO_SA_FACT) {
+    // second layer of a FACTORED SA scale: row (b,i,s) = relu(U[b, idx[b,i,s], :] - V[b, i, :]), where
+    // U = W1 . [f_j | x_j] for every POINT and V = W1x . c_i - bias1 for every CENTRE (the first layer is linear
+    // before its ReLU, so it is evaluated once per point instead of once per (centre, neighbour) pair)
+    if (k >= a.c_feat) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sts128(sa + sw128_off(r_first + 4 * j, sub), 0.f, 0.f, 0.f, 0.f);
+      return;
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {   // two halves: 8 LDG.128 in flight each
+      float4 u[4], v[4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = h * 4 + jj;
+        u[jj] = ldg128(s.row[j] + k);
+        v[jj] = ldg128(a.new_xyz + static_cast<size_t>(s.crow[j]) * a.ldf + k);
+      }
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = h * 4 + jj;
+        float4 r = make_float4(fmaxf(u[jj].x - v[jj].x, 0.f), fmaxf(u[jj].y - v[jj].y, 0.f),
+                               fmaxf(u[jj].z - v[jj].z, 0.f), fmaxf(u[jj].w - v[jj].w, 0.f));
+        if (!((s.live >> j) & 1u)) r = zero;
+        sts_tf32(sa + sw128_off(r_first + 4 * j, sub), r);
+      }
+    }
+    return;
+  }
   if (PRO == PRO_DENSE || PRO == PRO_SA_GATHER) {
     const int seg = PRO == PRO_DENSE ? a.a_cols : a.c_feat;        // vector-loadable prefix of the row
     const int end = PRO == PRO_DENSE ? a.a_cols : a.c_feat + 3;    // logical row length
@@ -1266,12 +1296,49 @@ int dispatch(MlpArgs &a, int pro, int pool, cudaStream_t st) {
     a.pool = pool;
     if (pro == PRO_DENSE) return launch_mlp<PRO_DENSE, EPI_MAXPOOL>(a, st);
     if (pro == PRO_SA_GATHER) return launch_mlp<PRO_SA_GATHER, EPI_MAXPOOL>(a, st);
+    if (pro == PRO_SA_FACT) return launch_mlp<PRO_SA_FACT, EPI_MAXPOOL>(a, st);
     return PVN3D_ERR_INVALID_ARG;
   }
   a.pool = 0;
   if (pro == PRO_DENSE) return launch_mlp<PRO_DENSE, EPI_STORE>(a, st);
+  if (pro == PRO_SA_FACT) return launch_mlp<PRO_SA_FACT, EPI_STORE>(a, st);
   if (pro == PRO_SA_GATHER) return launch_mlp<PRO_SA_GATHER, EPI_STORE>(a, st);
   return launch_mlp<PRO_FP_INTERP, EPI_STORE>(a, st);
+}
+
+// ---- factored first layer of an SA scale -------------------------------------------------------------
+// table row j = [ tf32(f_j) (C) | hi(x_j) (3) | lo(x_j) (3) | 0.. ]: x = hi + lo with hi = tf32(x), lo = tf32(x - hi),
+// so that a TF32 GEMM against [W_f | W_x | W_x] evaluates W_x . x to ~2^-21 relative (the coordinates are
+// ~1 m and their DIFFERENCES ~1 cm: a single TF32 rounding of x would cost 10 % of the difference)
+__global__ void sa_factor_table_kernel(const float *__restrict__ xyz, const float *__restrict__ feat, int ldf,
+                                       int c_feat, long long rows, int k_pad, float *__restrict__ out) {
+  const long long p = static_cast<long long>(blockIdx.x) * blockDim.y + threadIdx.y;
+  if (p >= rows) return;
+  float *o = out + p * k_pad;
+  for (int c = threadIdx.x; c < k_pad; c += blockDim.x) {
+    float v = 0.f;
+    if (c < c_feat) {
+      v = to_tf32(__ldg(feat + p * ldf + c));
+    } else if (c < c_feat + 6) {
+      const int d = (c - c_feat) % 3;
+      const float x = __ldg(xyz + p * 3 + d);
+      const float hi = to_tf32(x);
+      v = c < c_feat + 3 ? hi : to_tf32(x - hi);
+    }
+    o[c] = v;
+  }
+}
+// V[i, n] = sum_d Wx[n, d] * c_i[d] - bias[n]   (fp32 FMAs; Wx = the TF32-rounded xyz columns of W1)
+__global__ void sa_centre_term_kernel(const float *__restrict__ centres, const float *__restrict__ wx,
+                                      const float *__restrict__ bias, long long rows, int n_pad,
+                                      float *__restrict__ out) {
+  const long long p = static_cast<long long>(blockIdx.x) * blockDim.y + threadIdx.y;
+  if (p >= rows) return;
+  const float cx = __ldg(centres + p * 3), cy = __ldg(centres + p * 3 + 1), cz = __ldg(centres + p * 3 + 2);
+  for (int n = threadIdx.x; n < n_pad; n += blockDim.x) {
+    const float w0 = __ldg(wx + n * 3), w1 = __ldg(wx + n * 3 + 1), w2 = __ldg(wx + n * 3 + 2);
+    out[p * n_pad + n] = __fmaf_rn(w2, cz, __fmaf_rn(w1, cy, w0 * cx)) - __ldg(bias + n);
+  }
 }
 
 // inverse-distance weights of PointnetFPModule.forward (pointnet2_modules.py:183-186) + 3-NN indices
@@ -1418,4 +1485,47 @@ extern "C" int pvn3d_mlp_fp_chain(const float *known_feat_pm, int c2, const int 
   a.k_pad = layers[0].k_pad;
   chain_plan(c, layers, n_layers);
   return launch_chain<PRO_FP_INTERP, EPI_STORE>(c, workspace, workspace_bytes, as_stream(stream));
+}
+
+extern "C" int pvn3d_sa_factor_table(const float *xyz, const float *feat_pm, int ldf, int c_feat, long long rows,
+                                     int k_pad, float *out, pvn3d_stream_t stream) {
+  if (!xyz || !out || rows < 0 || c_feat < 0 || (c_feat > 0 && (!feat_pm || ldf < c_feat)) || k_pad < c_feat + 6 ||
+      k_pad % 32)
+    return PVN3D_ERR_INVALID_ARG;
+  if (rows == 0) return PVN3D_OK;
+  const dim3 block(32, 8);
+  sa_factor_table_kernel<<<static_cast<unsigned>((rows + 7) / 8), block, 0, as_stream(stream)>>>(xyz, feat_pm, ldf, c_feat,
+                                                                                                rows, k_pad, out);
+  return check_launch("sa_factor_table_kernel");
+}
+
+extern "C" int pvn3d_sa_centre_term(const float *centres, const float *wx, const float *bias, long long rows,
+                                    int n_pad, float *out, pvn3d_stream_t stream) {
+  if (!centres || !wx || !bias || !out || rows < 0 || n_pad <= 0 || n_pad % 4) return PVN3D_ERR_INVALID_ARG;
+  if (rows == 0) return PVN3D_OK;
+  const dim3 block(32, 8);
+  sa_centre_term_kernel<<<static_cast<unsigned>((rows + 7) / 8), block, 0, as_stream(stream)>>>(centres, wx, bias, rows,
+                                                                                               n_pad, out);
+  return check_launch("sa_centre_term_kernel");
+}
+
+extern "C" int pvn3d_mlp_sa_fact(const float *u, const float *v, int ldu, int c_valid, const int *idx, int b, int n,
+                                 int m, int ns, const float *w, const float *bias, int k_pad, int n_pad, int flags,
+                                 int pool, float *out, int ldo, int col0, pvn3d_stream_t stream) {
+  if (!u || !v || !idx || !w || !bias || !out || b < 0 || n <= 0 || m < 0 || ns <= 0 || c_valid <= 0 ||
+      c_valid % 4 || ldu < c_valid || ldu % 4 || k_pad < c_valid || ldo % 4 || col0 % 4 ||
+      (reinterpret_cast<uintptr_t>(u) & 15u) || (reinterpret_cast<uintptr_t>(v) & 15u))
+    return PVN3D_ERR_INVALID_ARG;
+  if (pool && pool != ns) return PVN3D_ERR_INVALID_ARG;
+  if (static_cast<long long>(m) * ns > 0x3fffffffll || static_cast<long long>(b) * n > 0x7fffffffll ||
+      static_cast<long long>(b) * m > 0x7fffffffll)
+    return PVN3D_ERR_UNSUPPORTED;
+  MlpArgs a{};
+  a.w = w; a.bias = bias; a.rows = static_cast<long long>(b) * m * ns; a.k_pad = k_pad; a.n_pad = n_pad;
+  a.feat = u; a.new_xyz = v; a.ldf = ldu; a.c_feat = c_valid; a.idx = idx;
+  a.n = n; a.m = m; a.ns = ns;
+  a.out = out; a.ldo = ldo; a.col0 = col0;
+  a.relu = flags & PVN3D_MLP_RELU; a.round_out = (flags & PVN3D_MLP_ROUND_OUT) ? 1 : 0;
+  a.reserve_sms = (flags >> 8) & 0xff;
+  return dispatch(a, PRO_SA_FACT, pool, as_stream(stream));
 }

@@ -122,6 +122,46 @@ def mlp_fp_first(known_feat_pm, nn_idx, nn_w, skip_ptr, lds, c1, layer: PackedLa
     return out
 
 
+def sa_factor_table(xyz: torch.Tensor, feat_ptr: int, ldf: int, c_feat: int, k_pad: int) -> torch.Tensor:
+    """[B,n,3] coordinates + point-major descriptors -> [B*n, k_pad] rows [tf32(f) | hi(x) | lo(x) | 0] (see
+    pvn3d_sa_factor_table in include/pvn3d_b200.h)"""
+    lib = _lib.load()
+    rows = xyz.size(0) * xyz.size(1)
+    out = torch.empty((rows, k_pad), dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        rc = lib.pvn3d_sa_factor_table(ptr(xyz), feat_ptr, ldf, c_feat, rows, k_pad, ptr(out), _stream(xyz.device))
+    check(rc, "pvn3d_sa_factor_table")
+    return out
+
+
+def sa_centre_term(new_xyz: torch.Tensor, wx: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """V[i] = Wx . c_i - bias for every sampled centre: new_xyz [B,m,3], wx [n_pad,3], bias [n_pad] -> [B*m, n_pad]"""
+    lib = _lib.load()
+    rows = new_xyz.size(0) * new_xyz.size(1)
+    n_pad = wx.size(0)
+    out = torch.empty((rows, n_pad), dtype=torch.float32, device=new_xyz.device)
+    with torch.cuda.device(new_xyz.device):
+        rc = lib.pvn3d_sa_centre_term(ptr(new_xyz), ptr(wx), ptr(bias), rows, n_pad, ptr(out), _stream(new_xyz.device))
+    check(rc, "pvn3d_sa_centre_term")
+    return out
+
+
+def mlp_sa_fact(u: torch.Tensor, v: torch.Tensor, idx: torch.Tensor, n: int, layer: PackedLayer, relu=True, pool=0,
+                out=None, col0=0, round_out=False, reserve=0):
+    """second layer of a factored SA scale: rows relu(U[idx] - V) -> layer (pvn3d_mlp_sa_fact)"""
+    lib = _lib.load()
+    b, m, ns = idx.shape
+    rows = b * m * ns
+    if out is None:
+        out = torch.empty((rows // pool if pool else rows, layer.n_pad), dtype=torch.float32, device=u.device)
+    with torch.cuda.device(u.device):
+        rc = lib.pvn3d_mlp_sa_fact(ptr(u), ptr(v), u.size(-1), u.size(-1), ptr(idx), b, n, m, ns, ptr(layer.w), ptr(layer.bias),
+                                   layer.k_pad, layer.n_pad, _flags(relu, round_out, reserve=reserve), pool, ptr(out),
+                                   out.size(-1), col0, _stream(u.device))
+    check(rc, "pvn3d_mlp_sa_fact")
+    return out
+
+
 class LayerChain:
     """the layers of one SharedMLP as the pvn3d_mlp_layer_t array pvn3d_mlp_{sa,fp}_chain take, plus the
     scratch the chained kernel needs (inter-layer tiles of the CTAs, L2-resident)"""
@@ -243,6 +283,23 @@ class FusedPointnet2MSG:
         #: store the level tables of SA1-3 TF32-rounded so that the next level gathers them with cp.async
         #: (identical features: every reader of those tables rounds on staging; PVN3D_MLP_ROUND_TABLES=0 disables)
         self.round_tables = (not self.chain) and os.environ.get("PVN3D_MLP_ROUND_TABLES", "1") != "0"
+        #: evaluate the first layer of every SA scale once per POINT instead of once per (centre, neighbour) pair
+        #: (it is linear before its ReLU).  PVN3D_MLP_FACTOR=0 keeps the gather-first layers.
+        self.factor = (not self.chain) and os.environ.get("PVN3D_MLP_FACTOR", "1") != "0"
+        self.sa_fact = []
+        for li, sa in enumerate(model.SA_modules):
+            per_scale = []
+            for si, mlp in enumerate(sa.mlps):
+                w, bias = fold_conv_bn(mlp[0])                    # reference column order [xyz(3) | features]
+                wf, wxyz = w[:, 3:], w[:, :3]
+                first = PackedLayer(torch.cat([wf, wxyz, wxyz], dim=1), torch.zeros_like(bias))   # [W_f | W_x | W_x], bias in V
+                n_pad = first.n_pad
+                wx = torch.zeros((n_pad, 3), dtype=torch.float32, device=self.dev)
+                wx[: w.size(0)] = tf32_round(wxyz.to(self.dev))
+                b1 = torch.zeros((n_pad,), dtype=torch.float32, device=self.dev)
+                b1[: w.size(0)] = bias.to(self.dev)
+                per_scale.append((first, wx.contiguous(), b1))
+            self.sa_fact.append(per_scale)
         self.sa_chain = [[LayerChain(layers) for layers in scales] for scales in self.sa] if self.chain else None
         self.fp_chain = [LayerChain(layers) for layers in self.fp] if self.chain else None
         self._marks = None
@@ -344,7 +401,25 @@ class FusedPointnet2MSG:
             fptr, ldf, c_feat = feats[-1]
             out_l = torch.empty((b, npoint, self.sa_out[li]), dtype=torch.float32, device=self.dev)
             col = 0
+            table = None
+            if self.factor and len(self.sa[li][0]) >= 2:
+                table = sa_factor_table(x, fptr, ldf, c_feat, self.sa_fact[li][0][0].k_pad)   # shared by both scales
             for si, (idx, ns, layers) in enumerate(zip(plan.ball[li], nsamples, self.sa[li])):
+                if table is not None:
+                    first, wx, b1 = self.sa_fact[li][si]
+                    u = mlp_dense(table, first, relu=False, a_tf32=True, reserve=rs)        # once per point
+                    v = sa_centre_term(new_xyz, wx, b1)                                     # once per centre
+                    last2 = len(layers) == 2
+                    h = mlp_sa_fact(u, v, idx, x.size(1), layers[1], pool=ns if last2 else 0, round_out=not last2 or
+                                    (self.round_tables and li < 3), reserve=rs,
+                                    out=out_l.view(b * npoint, -1) if last2 else None, col0=col if last2 else 0)
+                    if not last2:
+                        for mid in layers[2:-1]:
+                            h = mlp_dense(h, mid, round_out=True, a_tf32=True, reserve=rs)
+                        mlp_dense(h, layers[-1], pool=ns, out=out_l.view(b * npoint, -1), col0=col, a_tf32=True, reserve=rs,
+                                  round_out=self.round_tables and li < 3)
+                    col += layers[-1].n
+                    continue
                 if self.chain:
                     mlp_sa_chain(x, new_xyz, fptr, ldf, c_feat, idx, self.sa_chain[li][si], pool=ns,
                                  out=out_l.view(b * npoint, -1), col0=col, reserve=rs)

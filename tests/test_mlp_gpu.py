@@ -226,7 +226,9 @@ def test_chain_engine_equals_layer_engine_and_is_deterministic(cuda_dev):
     model = testing.seeded_pointnet2msg(0, 1)
     frames = synth.make_batch("ycb", 2, n_points=12288, config_id=13)
     x = torch.from_numpy(np.stack([f.cld_rgb_nrm for f in frames])).to(cuda_dev)
-    y_layer = mlp.FusedPointnet2MSG(model, cuda_dev, chain=False)(x)
+    layer_eng = mlp.FusedPointnet2MSG(model, cuda_dev, chain=False)
+    layer_eng.factor = False          # the chained kernel runs the unfactored first layer: same operands, same bits
+    y_layer = layer_eng(x)
     eng = mlp.FusedPointnet2MSG(model, cuda_dev, chain=True)
     y0 = eng(x).clone()
     assert torch.equal(y0, y_layer), float((y0 - y_layer).abs().max())
@@ -248,3 +250,28 @@ def test_rounded_level_tables_do_not_change_the_features(cuda_dev):
     eng.round_tables = False
     y_sync = eng(x)
     assert torch.equal(y_async, y_sync), float((y_async - y_sync).abs().max())
+
+
+def test_factored_first_layer_matches_unfactored_engine(cuda_dev, golden_dir):
+    """first SA layer evaluated once per point (U_j - V_i, coordinate term split hi + lo) vs once per grouped row with
+    the difference x_j - c_i rounded to TF32: same function, different rounding points -> TF32-class agreement; and the
+    factored engine is at least as close to the reference's fp32 features as the unfactored one"""
+    from pvn3d_b200 import synth
+
+    z = np.load(os.path.join(golden_dir, "pn2msg_big.npz"))
+    model = testing.seeded_pointnet2msg(0, 1)
+    x = torch.from_numpy(z["cld_rgb_nrm"])[None].to(cuda_dev)
+    eng = mlp.FusedPointnet2MSG(model, cuda_dev, chain=False)
+    assert eng.factor
+    y_fact = eng(x).clone()
+    eng.factor = False
+    y_plain = eng(x)
+    scale = float(y_plain.abs().mean())
+    d = (y_fact - y_plain).abs()
+    assert float(d.mean()) <= 3e-3 * scale and float(d.max()) <= 5e-2 * scale, (float(d.mean()) / scale, float(d.max()) / scale)
+    cols = torch.from_numpy(z["cols"]).long().to(cuda_dev)
+    ref = torch.from_numpy(z["feats"]).to(cuda_dev)
+    e_fact = float((y_fact[0][:, cols] - ref).abs().mean())
+    e_plain = float((y_plain[0][:, cols] - ref).abs().mean())
+    print(f"mean |err| vs reference fp32 features: factored {e_fact / scale:.2e}, unfactored {e_plain / scale:.2e}")
+    assert e_fact <= 1.2 * e_plain + 1e-6
