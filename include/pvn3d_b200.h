@@ -228,6 +228,15 @@ int pvn3d_sa_centre_term(const float *centres, const float *wx, const float *bia
 int pvn3d_mlp_sa_fact(const float *u, const float *v, int ldu, int c_valid, const int *idx, int b, int n, int m,
                       int ns, const float *w, const float *bias, int k_pad, int n_pad, int flags, int pool,
                       float *out, int ldo, int col0, pvn3d_stream_t stream);
+/* FACTORED first layer of an FP module: three_interpolate commutes with the (linear) first layer, so
+ *   P = W1k . known      once per KNOWN point   (pvn3d_mlp_dense without ReLU on the known table),
+ *   S = W1s . skip + b1  over the skip columns  (pvn3d_mlp_dense without ReLU on the skip table),
+ * and the second layer takes relu(sum_t nn_w[b,j,t] * P[b, nn_idx[b,j,t], :] + S[b,j,:]) as its operand:
+ * the gathered rows shrink from the known descriptors (256-1024 floats) to the layer width (128-512).
+ *   p [B*m_known, ld], s [B*n_unknown, ld], ld == c_valid (multiple of 4) */
+int pvn3d_mlp_fp_fact(const float *p, const float *s, int ld, int c_valid, const int *nn_idx, const float *nn_w,
+                      int b, int n_unknown, int m_known, const float *w, const float *bias, int k_pad, int n_pad,
+                      int flags, float *out, int ldo, int col0, pvn3d_stream_t stream);
 /* weight[p,0:3] = (1/(sqrt(dist2)+1e-8)) / sum  (pointnet2_modules.py:184-186), fp32 IEEE ops */
 int pvn3d_three_nn_weights(const float *dist2, long long rows, float *weight, pvn3d_stream_t stream);
 

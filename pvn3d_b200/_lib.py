@@ -75,6 +75,8 @@ _SIGNATURES = {
     "pvn3d_sa_centre_term": (c_int, [_P, _P, _P, ctypes.c_longlong, c_int, _P, _P]),
     "pvn3d_mlp_sa_fact": (c_int, [_P, _P, c_int, c_int, _P, c_int, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, c_int, _P,
                                   c_int, c_int, _P]),
+    "pvn3d_mlp_fp_fact": (c_int, [_P, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, _P, _P, c_int, c_int, c_int, _P, c_int, c_int,
+                                  _P]),
     "pvn3d_three_nn_weights": (c_int, [_P, ctypes.c_longlong, _P, _P]),
     "pvn3d_seg_argmax": (c_int, [_P, ctypes.c_longlong, c_int, _P, _P]),
     "pvn3d_pose_add_adds_workspace_bytes": (c_size_t, [c_int, c_int]),

@@ -41,7 +41,7 @@ constexpr int kMlpProWarps = 8;  // warps 4-11: two producer groups of 128 threa
 constexpr int kMlpThreads = (kMlpEpiWarps + kMlpProWarps + 1) * 32;  // warp 12: TMEM owner + MMA issuer
 constexpr int kMlpMaxStages = 6;
 
-enum : int { PRO_DENSE = 0, PRO_SA_GATHER = 1, PRO_FP_INTERP = 2, PRO_SA_FACT = 3 };
+enum : int { PRO_DENSE = 0, PRO_SA_GATHER = 1, PRO_FP_INTERP = 2, PRO_SA_FACT = 3, PRO_FP_FACT = 4 };
 enum : int { EPI_STORE = 0, EPI_MAXPOOL = 1 };
 
 struct MlpArgs {
@@ -275,6 +275,42 @@ __device__ __forceinline__ void stage_a_chunk(const MlpArgs &a, const RowState &
                                               int r_first, int sub, int k0, uint32_t sa, bool vec_ok) {
   const int k = k0 + 4 * sub;
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (PRO == PRO_FP_FACT) {
+    // second layer of a FACTORED FP module: row (b,j) = relu( sum_t w_t * P[b, idx_t, :] + S[b, j, :] ) with
+    // P = W1k . known (once per KNOWN point) and S = W1s . skip + b1 (the skip columns only): the first layer is
+    // linear before its ReLU, so three_interpolate commutes with it (pointnet2_modules.py:183-204)
+    if (k >= a.c2) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sts128(sa + sw128_off(r_first + 4 * j, sub), 0.f, 0.f, 0.f, 0.f);
+      return;
+    }
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {   // four quarters: 8 LDG.128 in flight each
+      float4 p1[2], p2[2], p3[2], sk[2];
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j = h * 2 + jj;
+        const float *pf = a.known_feat + k;
+        p1[jj] = ldg128(pf + static_cast<size_t>(s.g1[j]) * a.c2);
+        p2[jj] = ldg128(pf + static_cast<size_t>(s.g2[j]) * a.c2);
+        p3[jj] = ldg128(pf + static_cast<size_t>(s.g3[j]) * a.c2);
+        const long long pr = ((s.live >> j) & 1u) ? p_first + 4 * j : 0;
+        sk[jj] = ldg128(a.skip + pr * a.c2 + k);
+      }
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) {
+        const int j = h * 2 + jj;
+        float4 v;
+        v.x = fmaxf(__fmaf_rn(p3[jj].x, s.w3[j], __fmaf_rn(p1[jj].x, s.w1[j], __fmul_rn(p2[jj].x, s.w2[j]))) + sk[jj].x, 0.f);
+        v.y = fmaxf(__fmaf_rn(p3[jj].y, s.w3[j], __fmaf_rn(p1[jj].y, s.w1[j], __fmul_rn(p2[jj].y, s.w2[j]))) + sk[jj].y, 0.f);
+        v.z = fmaxf(__fmaf_rn(p3[jj].z, s.w3[j], __fmaf_rn(p1[jj].z, s.w1[j], __fmul_rn(p2[jj].z, s.w2[j]))) + sk[jj].z, 0.f);
+        v.w = fmaxf(__fmaf_rn(p3[jj].w, s.w3[j], __fmaf_rn(p1[jj].w, s.w1[j], __fmul_rn(p2[jj].w, s.w2[j]))) + sk[jj].w, 0.f);
+        if (!((s.live >> j) & 1u)) v = zero;
+        sts_tf32(sa + sw128_off(r_first + 4 * j, sub), v);
+      }
+    }
+    return;
+  }
   if (PRO == PRO_SA_FACT) {
     // second layer of a FACTORED SA scale: row (b,i,s) = relu(U[b, idx[b,i,s], :] - V[b, i, :]), where
     // U = W1 . [f_j | x_j] for every POINT and V = W1x . c_i - bias1 for every CENTRE (the first layer is linear
@@ -1302,6 +1338,7 @@ int dispatch(MlpArgs &a, int pro, int pool, cudaStream_t st) {
   a.pool = 0;
   if (pro == PRO_DENSE) return launch_mlp<PRO_DENSE, EPI_STORE>(a, st);
   if (pro == PRO_SA_FACT) return launch_mlp<PRO_SA_FACT, EPI_STORE>(a, st);
+  if (pro == PRO_FP_FACT) return launch_mlp<PRO_FP_FACT, EPI_STORE>(a, st);
   if (pro == PRO_SA_GATHER) return launch_mlp<PRO_SA_GATHER, EPI_STORE>(a, st);
   return launch_mlp<PRO_FP_INTERP, EPI_STORE>(a, st);
 }
@@ -1528,4 +1565,23 @@ extern "C" int pvn3d_mlp_sa_fact(const float *u, const float *v, int ldu, int c_
   a.relu = flags & PVN3D_MLP_RELU; a.round_out = (flags & PVN3D_MLP_ROUND_OUT) ? 1 : 0;
   a.reserve_sms = (flags >> 8) & 0xff;
   return dispatch(a, PRO_SA_FACT, pool, as_stream(stream));
+}
+
+extern "C" int pvn3d_mlp_fp_fact(const float *p, const float *s, int ld, int c_valid, const int *nn_idx,
+                                 const float *nn_w, int b, int n_unknown, int m_known, const float *w,
+                                 const float *bias, int k_pad, int n_pad, int flags, float *out, int ldo, int col0,
+                                 pvn3d_stream_t stream) {
+  if (!p || !s || !nn_idx || !nn_w || !w || !bias || !out || b < 0 || n_unknown < 0 || m_known <= 0 || c_valid <= 0 ||
+      c_valid % 4 || ld != c_valid || k_pad < c_valid || ldo % 4 || col0 % 4 || (reinterpret_cast<uintptr_t>(p) & 15u) ||
+      (reinterpret_cast<uintptr_t>(s) & 15u))
+    return PVN3D_ERR_INVALID_ARG;
+  if (static_cast<long long>(b) * m_known > 0x7fffffffll || n_unknown > 0x3fffffff) return PVN3D_ERR_UNSUPPORTED;
+  MlpArgs a{};
+  a.w = w; a.bias = bias; a.rows = static_cast<long long>(b) * n_unknown; a.k_pad = k_pad; a.n_pad = n_pad;
+  a.known_feat = p; a.c2 = ld; a.nn_idx = nn_idx; a.nn_w = nn_w; a.skip = s; a.lds = ld; a.c1 = 0;
+  a.n_unknown = n_unknown; a.m_known = m_known;
+  a.out = out; a.ldo = ldo; a.col0 = col0;
+  a.relu = flags & PVN3D_MLP_RELU; a.round_out = (flags & PVN3D_MLP_ROUND_OUT) ? 1 : 0;
+  a.reserve_sms = (flags >> 8) & 0xff;
+  return dispatch(a, PRO_FP_FACT, 0, as_stream(stream));
 }

@@ -162,6 +162,21 @@ def mlp_sa_fact(u: torch.Tensor, v: torch.Tensor, idx: torch.Tensor, n: int, lay
     return out
 
 
+def mlp_fp_fact(p: torch.Tensor, s_: torch.Tensor, nn_idx: torch.Tensor, nn_w: torch.Tensor, m_known: int,
+                layer: PackedLayer, relu=True, round_out=False, reserve=0):
+    """second layer of a factored FP module: rows relu(sum_t w_t P[idx_t] + S) -> layer (pvn3d_mlp_fp_fact)"""
+    lib = _lib.load()
+    b, n_unknown = nn_idx.shape[0], nn_idx.shape[1]
+    ld = p.size(-1)
+    out = torch.empty((b * n_unknown, layer.n_pad), dtype=torch.float32, device=p.device)
+    with torch.cuda.device(p.device):
+        rc = lib.pvn3d_mlp_fp_fact(ptr(p), ptr(s_), ld, ld, ptr(nn_idx), ptr(nn_w), b, n_unknown, m_known, ptr(layer.w),
+                                   ptr(layer.bias), layer.k_pad, layer.n_pad, _flags(relu, round_out, reserve=reserve),
+                                   ptr(out), out.size(-1), 0, _stream(p.device))
+    check(rc, "pvn3d_mlp_fp_fact")
+    return out
+
+
 class LayerChain:
     """the layers of one SharedMLP as the pvn3d_mlp_layer_t array pvn3d_mlp_{sa,fp}_chain take, plus the
     scratch the chained kernel needs (inter-layer tiles of the CTAs, L2-resident)"""
@@ -300,6 +315,18 @@ class FusedPointnet2MSG:
                 b1[: w.size(0)] = bias.to(self.dev)
                 per_scale.append((first, wx.contiguous(), b1))
             self.sa_fact.append(per_scale)
+        # factored FP first layers: W1 = [W_k (known columns) | W_s (skip columns)]
+        self.fp_fact = []
+        skip_c = [model.SA_modules[0].mlps[0][0].conv.weight.size(1) - 3] + self.sa_out[:3]     # skip widths of FP1..FP4
+        for i, fp in enumerate(model.FP_modules):
+            w, bias = fold_conv_bn(fp.mlp[0])
+            c1 = skip_c[i]
+            c2 = w.size(1) - c1
+            lk = PackedLayer(w[:, :c2].contiguous(), torch.zeros_like(bias))
+            ws = w[:, c2:]
+            if i == 0:     # the skip of FP1 is the raw cloud (ld 9): read it through the level-0 factor table [f | hi x | lo x]
+                ws = torch.cat([ws, torch.zeros((w.size(0), 6), dtype=ws.dtype, device=ws.device)], dim=1)
+            self.fp_fact.append((lk, PackedLayer(ws.contiguous(), bias), c2))
         self.sa_chain = [[LayerChain(layers) for layers in scales] for scales in self.sa] if self.chain else None
         self.fp_chain = [LayerChain(layers) for layers in self.fp] if self.chain else None
         self._marks = None
@@ -396,6 +423,7 @@ class FusedPointnet2MSG:
         feats: List[Tuple[int, int, int]] = [(pointcloud.data_ptr() + 12, width, c0)]   # (address, ld, channels)
         keep = [pointcloud]
         l_xyz = plan.l_xyz
+        table0 = None
         for li, (npoint, radii, nsamples, _) in enumerate(SA_SPEC):
             x, new_xyz = l_xyz[li], l_xyz[li + 1]
             fptr, ldf, c_feat = feats[-1]
@@ -404,6 +432,8 @@ class FusedPointnet2MSG:
             table = None
             if self.factor and len(self.sa[li][0]) >= 2:
                 table = sa_factor_table(x, fptr, ldf, c_feat, self.sa_fact[li][0][0].k_pad)   # shared by both scales
+                if li == 0:
+                    table0 = table
             for si, (idx, ns, layers) in enumerate(zip(plan.ball[li], nsamples, self.sa[li])):
                 if table is not None:
                     first, wx, b1 = self.sa_fact[li][si]
@@ -449,7 +479,17 @@ class FusedPointnet2MSG:
                 known_feat = known_feat.view(b, known.size(1), -1)
             sptr, lds, c1 = feats[i]
             layers = self.fp[i]
-            if self.chain:
+            # FP factoring pays only where the known descriptors are much wider than the layer and the skip is narrow:
+            # FP1 (256 + 6 -> 128 at 12288 points): 382 vs 420 us; FP2-4 measured 10-40 % SLOWER
+            if self.factor and len(layers) == 2 and i == 0 and table0 is not None:
+                lk, ls, c2 = self.fp_fact[i]
+                kf2d = known_feat.reshape(-1, known_feat.size(-1))
+                assert kf2d.size(-1) == c2
+                pk = mlp_dense(kf2d, lk, relu=False, reserve=rs)                                   # once per known point
+                skip2d = table0 if i == 0 else keep[i].view(-1, keep[i].size(-1))
+                sk = mlp_dense(skip2d, ls, relu=False, reserve=rs, a_tf32=(i == 0) or self.round_tables)
+                h = mlp_fp_fact(pk, sk, nn_idx, nn_w, known.size(1), layers[1], round_out=False, reserve=rs)
+            elif self.chain:
                 h = mlp_fp_chain(known_feat, nn_idx, nn_w, sptr, lds, c1, self.fp_chain[i], reserve=rs)
             else:
                 h = mlp_fp_first(known_feat, nn_idx, nn_w, sptr, lds, c1, layers[0], round_out=True, reserve=rs)
