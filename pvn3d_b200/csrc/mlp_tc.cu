@@ -320,23 +320,22 @@ __device__ __forceinline__ void stage_a_chunk(const MlpArgs &a, const RowState &
       for (int j = 0; j < 8; ++j) sts128(sa + sw128_off(r_first + 4 * j, sub), 0.f, 0.f, 0.f, 0.f);
       return;
     }
+    // the thread's 8 rows are 4 apart inside one 32-row block: at most two centres (nsample 16), one for nsample 32:
+    // two V loads + all eight U loads are in flight together
+    const float4 va = ldg128(a.new_xyz + static_cast<size_t>(s.crow[0]) * a.ldf + k);
+    const float4 vb = ldg128(a.new_xyz + static_cast<size_t>(s.crow[4]) * a.ldf + k);
+    float4 u[8];
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {   // two halves: 8 LDG.128 in flight each
-      float4 u[4], v[4];
+    for (int j = 0; j < 8; ++j) u[j] = ldg128(s.row[j] + k);
+    const bool two = a.ns % 16 == 0;   // 16-row groups never straddle centres: rows j < 4 share crow[0], j >= 4 crow[4]
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int j = h * 4 + jj;
-        u[jj] = ldg128(s.row[j] + k);
-        v[jj] = ldg128(a.new_xyz + static_cast<size_t>(s.crow[j]) * a.ldf + k);
-      }
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        const int j = h * 4 + jj;
-        float4 r = make_float4(fmaxf(u[jj].x - v[jj].x, 0.f), fmaxf(u[jj].y - v[jj].y, 0.f),
-                               fmaxf(u[jj].z - v[jj].z, 0.f), fmaxf(u[jj].w - v[jj].w, 0.f));
-        if (!((s.live >> j) & 1u)) r = zero;
-        sts_tf32(sa + sw128_off(r_first + 4 * j, sub), r);
-      }
+    for (int j = 0; j < 8; ++j) {
+      float4 v = j < 4 ? va : vb;
+      if (!two) v = ldg128(a.new_xyz + static_cast<size_t>(s.crow[j]) * a.ldf + k);   // other nsample: per-row centre
+      float4 r = make_float4(fmaxf(u[j].x - v.x, 0.f), fmaxf(u[j].y - v.y, 0.f), fmaxf(u[j].z - v.z, 0.f),
+                             fmaxf(u[j].w - v.w, 0.f));
+      if (!((s.live >> j) & 1u)) r = zero;
+      sts_tf32(sa + sw128_off(r_first + 4 * j, sub), r);
     }
     return;
   }

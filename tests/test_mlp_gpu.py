@@ -275,3 +275,61 @@ def test_factored_first_layer_matches_unfactored_engine(cuda_dev, golden_dir):
     e_plain = float((y_plain[0][:, cols] - ref).abs().mean())
     print(f"mean |err| vs reference fp32 features: factored {e_fact / scale:.2e}, unfactored {e_plain / scale:.2e}")
     assert e_fact <= 1.2 * e_plain + 1e-6
+
+
+@pytest.mark.parametrize("b,n,m,ns,c_feat,n1,n2", [(2, 1024, 300, 16, 96, 64, 96), (1, 512, 100, 32, 6, 32, 32),
+                                                    (3, 700, 129, 8, 256, 128, 208), (2, 2048, 512, 32, 512, 256, 384)])
+def test_factored_sa_first_layer_kernels(cuda_dev, b, n, m, ns, c_feat, n1, n2):
+    """pvn3d_sa_factor_table + pvn3d_mlp_dense (U) + pvn3d_sa_centre_term (V): U[idx] - V == W1.[f | x - c] + b1 to fp32
+    accuracy (the hi/lo coordinate split), and pvn3d_mlp_sa_fact == relu(tf32(relu(U[idx] - V)) . W2 + b2)"""
+    rng = np.random.default_rng(b + n + ns)
+    xyz = torch.from_numpy(rng.uniform(-0.5, 1.2, (b, n, 3)).astype(np.float32)).to(cuda_dev)
+    sel = torch.from_numpy(np.stack([rng.choice(n, m, replace=False) for _ in range(b)])).to(cuda_dev)
+    new_xyz = torch.gather(xyz, 1, sel[..., None].expand(-1, -1, 3)).contiguous()
+    idx = torch.from_numpy(rng.integers(0, n, (b, m, ns)).astype(np.int32)).to(cuda_dev)
+    feat = torch.from_numpy(rng.normal(size=(b, n, c_feat)).astype(np.float32)).to(cuda_dev)
+    g = torch.Generator().manual_seed(n + m)
+    w1 = (torch.randn(n1, c_feat + 3, generator=g) / np.sqrt(c_feat + 3)).to(cuda_dev)     # producer order [f | xyz]
+    b1 = (torch.randn(n1, generator=g) * 0.1).to(cuda_dev)
+    first = mlp.PackedLayer(torch.cat([w1, w1[:, c_feat:]], 1), torch.zeros_like(b1))         # [W_f | W_x | W_x]
+    wx = mlp.tf32_round(w1[:, c_feat:].contiguous())
+    wxp = torch.zeros((first.n_pad, 3), device=cuda_dev); wxp[:n1] = wx
+    b1p = torch.zeros((first.n_pad,), device=cuda_dev); b1p[:n1] = b1
+    table = mlp.sa_factor_table(xyz, feat.data_ptr(), c_feat, c_feat, first.k_pad)
+    u = mlp.mlp_dense(table, first, relu=False, a_tf32=True)
+    v = mlp.sa_centre_term(new_xyz, wxp, b1p)
+    bi = torch.arange(b, device=cuda_dev)[:, None, None]
+    got1 = (u.view(b, n, -1)[bi, idx.long()] - v.view(b, m, 1, -1))[..., :n1]                  # pre-ReLU first layer
+    f64 = mlp.tf32_round(feat).double()[bi, idx.long()]
+    dx = xyz.double()[bi, idx.long()] - new_xyz.double()[:, :, None, :]
+    want1 = f64 @ mlp.tf32_round(w1[:, :c_feat]).double().t() + dx @ wx.double().t() + b1.double()
+    assert float((got1.double() - want1).abs().max()) <= 2e-5 * max(1.0, float(want1.abs().max()))
+    # second layer on relu(U[idx] - V)
+    w2 = (torch.randn(n2, n1, generator=g) / np.sqrt(n1)).to(cuda_dev)
+    b2 = (torch.randn(n2, generator=g) * 0.1).to(cuda_dev)
+    l2 = mlp.PackedLayer(w2, b2, first.n_pad)
+    got2 = mlp.mlp_sa_fact(u, v, idx, n, l2)
+    a2 = mlp.tf32_round(torch.relu(u.view(b, n, -1)[bi, idx.long()] - v.view(b, m, 1, -1)).reshape(-1, first.n_pad)[:, :n1])
+    want2 = ref_dense(a2.cpu(), mlp.tf32_round(w2).cpu(), b2.cpu(), True, 0)
+    assert (got2.cpu()[:, :n2] - want2).abs().max() <= 2e-5 * max(1.0, float(want2.abs().max()))
+    got2p = mlp.mlp_sa_fact(u, v, idx, n, l2, pool=ns)
+    assert torch.equal(got2p, got2.view(b * m, ns, -1).max(1).values)
+
+
+def test_factored_fp_first_layer_kernel(cuda_dev):
+    rng = np.random.default_rng(9)
+    b_, n_u, m_k, n1, n2 = 2, 1000, 333, 128, 128
+    nn = torch.from_numpy(rng.integers(0, m_k, (b_, n_u, 3)).astype(np.int32)).to(cuda_dev)
+    w = rng.uniform(0.05, 1, (b_, n_u, 3)).astype(np.float32)
+    w = torch.from_numpy(w / w.sum(-1, keepdims=True)).to(cuda_dev)
+    p = torch.from_numpy(rng.normal(size=(b_ * m_k, n1)).astype(np.float32)).to(cuda_dev)
+    s_ = torch.from_numpy(rng.normal(size=(b_ * n_u, n1)).astype(np.float32)).to(cuda_dev)
+    g = torch.Generator().manual_seed(4)
+    l2 = mlp.PackedLayer((torch.randn(n2, n1, generator=g) / np.sqrt(n1)).to(cuda_dev), (torch.randn(n2, generator=g) * 0.1).to(cuda_dev), n1)
+    got = mlp.mlp_fp_fact(p, s_, nn, w, m_k, l2)
+    bi = torch.arange(b_, device=cuda_dev)[:, None, None]
+    pg = p.view(b_, m_k, n1)[bi, nn.long()]                                                     # [b, n, 3, n1]
+    a = torch.relu((pg[:, :, 2] * w[..., 2:3]).add(pg[:, :, 0] * w[..., 0:1] + pg[:, :, 1] * w[..., 1:2]) + s_.view(b_, n_u, n1))
+    want = ref_dense(mlp.tf32_round(a.reshape(-1, n1)).cpu(), l2.w.cpu()[:n2, :n1], l2.bias.cpu()[:n2], True, 0)
+    # interpolation order differs in the last ulp before TF32 rounding: one TF32 ulp of the operands
+    assert (got.cpu()[:, :n2] - want).abs().max() <= 1e-3 * max(1.0, float(want.abs().max()))
