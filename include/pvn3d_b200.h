@@ -258,6 +258,9 @@ int pvn3d_three_nn_weights(const float *dist2, long long rows, float *weight, pv
  * C_T.  ctr.w reports it0 (a lower bound of the reference's T).  Fits that cannot be certified fall
  * back to PVN3D_MS_EARLY_EXIT over all seeds, which applies the reference's rule exactly. */
 #define PVN3D_MS_CERTIFIED 8u
+/* validation: count the inliers of every input point by the brute-force n^2 pass instead of the pruned one
+ * (radial sort + triangle inequality; both are exact and must agree bit for bit) */
+#define PVN3D_MS_BRUTE_DENSITY 16u
 
 /* A batch of F independent MeanShiftTorch(bandwidth, max_iter).fit(A_f) problems.
  *   pts        [cap,4] f32  vote clouds (x,y,z,unused); fit f owns rows
@@ -278,6 +281,9 @@ int pvn3d_three_nn_weights(const float *dist2, long long rows, float *weight, pv
  * Semantics follow meanshift_pytorch.py:24-51 (stop when max_i |dC_i| < bandwidth*1e-3 or
  * it > max_iter; densest *input* point selects the returned seed; first-index arg-max). */
 size_t pvn3d_meanshift_workspace_bytes(int cap, int n_fits, int max_iter);
+/* byte offset, inside a pvn3d_meanshift_fit_batch workspace, of the int32 inlier count of every input point
+ * (indexed like pts) left by the exact pass of the last launch -- test / diagnostics access */
+size_t pvn3d_meanshift_workspace_counts_offset(int cap, int n_fits, int max_iter);
 int pvn3d_meanshift_fit_batch(const float *pts, const int *fit_start, const int *fit_count,
                               int n_fits, int cap, double bandwidth, int max_iter, unsigned flags,
                               float *ctr, uint8_t *labels, int *max_idx, int *n_in,

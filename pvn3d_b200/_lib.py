@@ -17,6 +17,7 @@ PVN3D_MS_EARLY_EXIT = 1
 PVN3D_MS_NO_FREEZE = 2
 PVN3D_MS_DEBUG_TIMING = 4
 PVN3D_MS_CERTIFIED = 8
+PVN3D_MS_BRUTE_DENSITY = 16
 PVN3D_MS_STAT_CERTIFIED = 8   # int32 word of the mean-shift workspace: fits closed by the witness kernel
 
 #: mode name -> flags of the mean-shift iteration (include/pvn3d_b200.h)
@@ -82,6 +83,7 @@ _SIGNATURES = {
     "pvn3d_pose_add_adds_workspace_bytes": (c_size_t, [c_int, c_int]),
     "pvn3d_pose_add_adds": (c_int, [_P, _P, c_int, _P, c_int, _P, _P, _P, c_size_t, _P]),
     "pvn3d_meanshift_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "pvn3d_meanshift_workspace_counts_offset": (c_size_t, [c_int, c_int, c_int]),
     "pvn3d_meanshift_fit_batch": (c_int, [_P, _P, _P, c_int, c_int, c_double, c_int, c_uint, _P, _P, _P, _P, _P, c_size_t, _P]),
     "pvn3d_best_fit_transform_batch": (c_int, [_P, _P, _P, c_int, c_int, _P, _P]),
     "pvn3d_frame_poses_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),

@@ -43,6 +43,8 @@ constexpr int kMsDensTile = 1024;  // points per tile of the density pass (16 KB
 constexpr int kMsWarps = kMsThreads / 32;
 constexpr int kMsCfgInts = 4096;   // [0..2] phase tickets, [3] grid barrier, [4..2047] debug, [2048..] CTAs seen per SM
 constexpr int kMsCfgSm = 2048;
+constexpr int kMsPruneMax = 4096;   // points per fit the pruned density kernel keeps in shared memory
+constexpr int kMsPruneBins = 2048;  // radial bins of its counting sort
 constexpr int kMsCfgCertified = 8;  // statistics of the last launch: fits closed by ms_witness_kernel
 
 struct MsArgs {
@@ -75,6 +77,8 @@ struct MsArgs {
   int *dens_prefix;  // [n_fits+1]
   int *dens_cnt;     // [cap] inlier count of every input point (exact pass); witness selection
   float delta_path;  // certified mode: the returned seed's remaining path at it0 is below this
+  int dens_pruned;   // fits of <= kMsPruneMax points are counted by ms_density_pruned_kernel
+  float bwf;         // float(bandwidth)
   int *cfg;          // [0..2] ticket counters of the phases
   int cap;
   int viol_words;
@@ -173,6 +177,7 @@ __global__ void __launch_bounds__(kMsThreads) ms_density_kernel(MsArgs a) {
   if (tile >= a.dens_prefix[a.n_fits]) return;
   const int f = find_segment(a.dens_prefix, a.n_fits, tile);
   const int start = a.fit_start[f], cnt = a.fit_count[f];
+  if (a.dens_pruned && cnt <= kMsPruneMax) return;   // ms_density_pruned_kernel counts this fit
   const int i = (tile - a.dens_prefix[f]) * kMsThreads + threadIdx.x;
   const bool live = i < cnt;
   const float4 me = a.pts[start + (live ? i : 0)];
@@ -219,6 +224,183 @@ __global__ void __launch_bounds__(kMsThreads) ms_density_kernel(MsArgs a) {
 #pragma unroll
     for (int w = 1; w < kMsWarps; ++w) key = s_key[w] > key ? s_key[w] : key;
     atomicMax(a.best_key + f, key);  // (count desc, index asc): torch.max first-index rule (:49)
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact density pass WITHOUT n^2 tests: num_in_i = #{j : |A_i - A_j| < bw} (meanshift_pytorch.py:46-48).
+//
+// Votes are a tight cluster plus scattered outliers.  With r_i = |A_i - c| for a pivot c near the cluster, the
+// triangle inequality decides most pairs without looking at them:
+//     r_i + r_j < bw - eps    =>  |A_i - A_j| < bw      (certainly an inlier of i)
+//     |r_i - r_j| > bw + eps  =>  |A_i - A_j| > bw      (certainly not)
+// One CTA per fit sorts its points by r (counting sort over radial bins, all in shared memory); point i then
+// needs   count_i = #{j : r_j < bw - eps - r_i}   -- a prefix sum, no distance evaluated --   plus an exact test
+// (the same fp32 contraction and threshold as the brute-force pass) of the points whose r_j lies in the band
+// [max(bw - eps - r_i, r_i - bw - eps), r_i + bw + eps].  For an inlier (r_i ~ 1 cm, bw = 8 cm) the band holds the
+// few outliers 7-9 cm from the pivot; for an outlier it is a thin shell of other outliers.  eps (0.1 mm + 1e-5 of
+// the cloud's radius) dwarfs every fp32 rounding involved, so each pair gets exactly the verdict the brute-force
+// test would give: counts, arg-max and labels stay bit-exact (tests: all golden cases + a direct comparison
+// against the brute-force kernel).  The pivot only steers how much is pruned, never the result: three rounds of
+// "mean of the points near the current estimate" starting from the centroid.
+struct MsPruneSmem {
+  float4 pts[kMsPruneMax];        // original order: x, y, z, r
+  int idx_sorted[kMsPruneMax];    // point indices in order of increasing radius
+  int cursor[kMsPruneBins];       // scatter cursors of the counting sort
+  int bin_start[kMsPruneBins + 1];
+  float red[kMsWarps][4];
+  float4 pivot;
+  float max_r;
+  unsigned long long key[kMsWarps];
+};
+
+__device__ __forceinline__ float4 ms_block_sum4(MsPruneSmem &sm, float4 v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+    v.z += __shfl_xor_sync(0xffffffffu, v.z, o);
+    v.w += __shfl_xor_sync(0xffffffffu, v.w, o);
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+    sm.red[threadIdx.x >> 5][0] = v.x; sm.red[threadIdx.x >> 5][1] = v.y;
+    sm.red[threadIdx.x >> 5][2] = v.z; sm.red[threadIdx.x >> 5][3] = v.w;
+  }
+  __syncthreads();
+  float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int w = 0; w < kMsWarps; ++w) {
+    t.x += sm.red[w][0]; t.y += sm.red[w][1]; t.z += sm.red[w][2]; t.w += sm.red[w][3];
+  }
+  return t;   // identical in every thread
+}
+
+__global__ void __launch_bounds__(kMsThreads, 2) ms_density_pruned_kernel(MsArgs a) {
+  extern __shared__ __align__(16) unsigned char ms_smem_raw[];
+  MsPruneSmem &sm = *reinterpret_cast<MsPruneSmem *>(ms_smem_raw);
+  const int f = blockIdx.x;
+  const int n = a.fit_count[f];
+  if (n <= 0 || n > kMsPruneMax) return;
+  const int start = a.fit_start[f];
+  const int t = threadIdx.x;
+  const float bw = a.bwf, t2 = a.t2;
+
+  // ---- points into shared memory, pivot = robust centre ------------------------------------------------
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = t; i < n; i += kMsThreads) {
+    const float4 p = a.pts[start + i];
+    sm.pts[i] = make_float4(p.x, p.y, p.z, 0.f);
+    acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += 1.f;
+  }
+  float4 sum = ms_block_sum4(sm, acc);
+  float3 c = make_float3(sum.x / sum.w, sum.y / sum.w, sum.z / sum.w);
+#pragma unroll 1
+  for (int round = 0; round < 2; ++round) {
+    const float rad = round == 0 ? 2.f * bw : bw;
+    acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = t; i < n; i += kMsThreads) {
+      const float4 p = sm.pts[i];
+      const float dx = p.x - c.x, dy = p.y - c.y, dz = p.z - c.z;
+      if (dx * dx + dy * dy + dz * dz < rad * rad) { acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += 1.f; }
+    }
+    sum = ms_block_sum4(sm, acc);
+    if (sum.w > 0.f) c = make_float3(sum.x / sum.w, sum.y / sum.w, sum.z / sum.w);
+  }
+
+  // ---- radii, bins, counting sort by radius ---------------------------------------------------------------
+  float rmax = 0.f;
+  for (int i = t; i < n; i += kMsThreads) {
+    float4 p = sm.pts[i];
+    const float dx = p.x - c.x, dy = p.y - c.y, dz = p.z - c.z;
+    p.w = sqrtf(dx * dx + dy * dy + dz * dz);
+    sm.pts[i] = p;
+    rmax = fmaxf(rmax, p.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+  __syncthreads();
+  if ((t & 31) == 0) sm.red[t >> 5][0] = rmax;
+  for (int b = t; b <= kMsPruneBins; b += kMsThreads) sm.bin_start[b] = 0;
+  __syncthreads();
+  rmax = sm.red[0][0];
+#pragma unroll
+  for (int w = 1; w < kMsWarps; ++w) rmax = fmaxf(rmax, sm.red[w][0]);
+  const float eps = 1e-4f + 1e-5f * (rmax + fabsf(c.x) + fabsf(c.y) + fabsf(c.z));
+  const float inv_w = static_cast<float>(kMsPruneBins) / (rmax * 1.0001f + 1e-20f);
+  auto bin_of = [&](float r) {
+    const float x = r * inv_w;   // may be huge when every point coincides (rmax = 0): clamp before the conversion
+    return x >= static_cast<float>(kMsPruneBins - 1) ? kMsPruneBins - 1 : max(0, static_cast<int>(x));
+  };
+  for (int i = t; i < n; i += kMsThreads) atomicAdd(&sm.bin_start[bin_of(sm.pts[i].w) + 1], 1);   // histogram, shifted by one
+  __syncthreads();
+  {  // inclusive scan of the shifted histogram = exclusive bin starts; 8 bins per thread
+    constexpr int per = kMsPruneBins / kMsThreads;
+    int local[per];
+    int s_ = 0;
+#pragma unroll
+    for (int q = 0; q < per; ++q) { s_ += sm.bin_start[1 + t * per + q]; local[q] = s_; }
+    int incl = s_;
+    const unsigned lane = t & 31u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += u;
+    }
+    __shared__ int s_warp[kMsWarps];
+    if (lane == 31) s_warp[t >> 5] = incl;
+    __syncthreads();
+    int base = incl - s_;
+    for (int w = 0; w < (t >> 5); ++w) base += s_warp[w];
+#pragma unroll
+    for (int q = 0; q < per; ++q) sm.bin_start[1 + t * per + q] = base + local[q];
+  }
+  __syncthreads();
+  // scatter: cursor per bin = its start (kept in r_sorted's storage as ints until the points land)
+  int *cursor = sm.cursor;
+  for (int b = t; b < kMsPruneBins; b += kMsThreads) cursor[b] = sm.bin_start[b];
+  __syncthreads();
+  for (int i = t; i < n; i += kMsThreads) {
+    const int pos = atomicAdd(&cursor[bin_of(sm.pts[i].w)], 1);
+    sm.idx_sorted[pos] = i;
+  }
+  __syncthreads();
+
+  // ---- counts ---------------------------------------------------------------------------------------------
+  const float bw_lo = bw - eps, bw_hi = bw + eps;
+  unsigned long long best = 0ull;
+  for (int q = t; q < n; q += kMsThreads) {   // consecutive threads = consecutive radii: similar bands inside a warp
+    const int i = sm.idx_sorted[q];
+    const float4 me = sm.pts[i];
+    const float lo = bw_lo - me.w, hi = me.w + bw_hi;
+    int count = 0, first = 0;
+    if (lo > 0.f) {
+      first = sm.bin_start[bin_of(lo)];       // every point of an earlier bin has r_j < lo: certainly within bw of i
+      count = first;
+    } else {
+      first = sm.bin_start[bin_of(fmaxf(me.w - bw_hi, 0.f))];   // earlier bins: r_j < r_i - bw - eps, certainly outside
+    }
+    const int last = hi * inv_w >= static_cast<float>(kMsPruneBins) ? n : sm.bin_start[bin_of(hi) + 1];
+    for (int pos = first; pos < last; ++pos) {
+      const float4 p = sm.pts[sm.idx_sorted[pos]];
+      // dis = torch.norm(Ar - Cr): diff = A_j - A_i, exactly as the brute-force pass
+      count += torch_sqnorm(p.x - me.x, p.y - me.y, p.z - me.z) < t2 ? 1 : 0;
+    }
+    a.dens_cnt[start + i] = count;
+    const unsigned long long key = (static_cast<unsigned long long>(count) << 32) | (0xFFFFFFFFu - static_cast<unsigned>(i));
+    best = key > best ? key : best;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+    best = other > best ? other : best;
+  }
+  if ((t & 31) == 0) sm.key[t >> 5] = best;
+  __syncthreads();
+  if (t == 0) {
+#pragma unroll
+    for (int w = 1; w < kMsWarps; ++w) best = sm.key[w] > best ? sm.key[w] : best;
+    a.best_key[f] = best;   // (count desc, index asc): torch.max first-index rule (:49); the only writer for this fit
   }
 }
 
@@ -1166,7 +1348,19 @@ int meanshift_launch(const float4 *pts, const int *fit_start, const int *fit_cou
     if ((rc = check_launch("ms_setup_kernel")) != PVN3D_OK) return rc;
     // upper bound on density tiles: every fit wastes < 1 tile
     const int tiles = ceil_div(cap, kMsThreads) + nf;
-    ms_density_kernel<<<tiles, kMsThreads, 0, st>>>(a);
+    static const bool prune_env = [] { const char *e = getenv("PVN3D_MS_PRUNED_DENSITY"); return !(e && e[0] == '0'); }();
+    a.dens_pruned = (prune_env && !(flags & PVN3D_MS_BRUTE_DENSITY)) ? 1 : 0;
+    a.bwf = bwf;
+    if (a.dens_pruned) {
+      static PerDeviceOnce once_pr;
+      PVN3D_ONCE_PER_DEVICE(once_pr,
+                            cudaFuncSetAttribute(ms_density_pruned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)sizeof(MsPruneSmem)),
+                            "ms_density_pruned smem attr");
+      ms_density_pruned_kernel<<<nf, kMsThreads, sizeof(MsPruneSmem), st>>>(a);
+      if ((rc = check_launch("ms_density_pruned_kernel")) != PVN3D_OK) return rc;
+    }
+    ms_density_kernel<<<tiles, kMsThreads, 0, st>>>(a);   // fits above kMsPruneMax points (all fits without pruning)
     if ((rc = check_launch("ms_density_kernel")) != PVN3D_OK) return rc;
     ms_prepare_kernel<<<tiles, kMsThreads, 0, st>>>(a);
     if ((rc = check_launch("ms_prepare_kernel")) != PVN3D_OK) return rc;
@@ -1227,4 +1421,9 @@ extern "C" int pvn3d_meanshift_fit_batch(const float *pts, const int *fit_start,
                           bandwidth, max_iter, flags, reinterpret_cast<float4 *>(ctr), labels,
                           max_idx, n_in, static_cast<unsigned char *>(workspace),
                           pvn3d::as_stream(stream), false);
+}
+
+extern "C" size_t pvn3d_meanshift_workspace_counts_offset(int cap, int n_fits, int max_iter) {
+  if (cap < 0 || n_fits < 0 || max_iter < 0 || max_iter > 4094) return 0;
+  return pvn3d::ms_layout(cap, n_fits, max_iter).dens_cnt;
 }

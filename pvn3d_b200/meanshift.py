@@ -37,6 +37,8 @@ class MeanShiftTorch:
         #:   "strict"     all seeds, reference stop rule: last_iters equals the reference's iteration count
         #:   "no_freeze"  strict + every seed swept at every iteration (the literal reference schedule)
         self.flags = ms_flags(mode, early_exit, no_freeze)
+        #: validation: brute-force n^2 density pass instead of the pruned one (PVN3D_MS_BRUTE_DENSITY)
+        self.brute_density = False
         self.debug_timing = False
         self.last_iters = None  # iteration count(s) of the last call, device tensor
 
@@ -89,7 +91,8 @@ class MeanShiftTorch:
             raise ValueError("max_iter must be in [0, 4094]")
         ws = torch.empty((ws_bytes + 256,), dtype=torch.uint8, device=dev)
         ws_ptr = (ws.data_ptr() + 255) // 256 * 256
-        flags = self.flags | (PVN3D_MS_DEBUG_TIMING if self.debug_timing else 0)
+        flags = self.flags | (PVN3D_MS_DEBUG_TIMING if self.debug_timing else 0) | (_lib.PVN3D_MS_BRUTE_DENSITY if self.brute_density else 0)
+        self._last_cap_nf = (cap, nf)
         with torch.cuda.device(dev):
             rc = lib.pvn3d_meanshift_fit_batch(
                 ptr(pts4), ptr(fit_start), ptr(fit_count), nf, cap, float(self.bandwidth),
@@ -105,3 +108,10 @@ class MeanShiftTorch:
         """diagnostics (synchronises): fits of the last call closed by the witness kernel"""
         ws, off = self._last_ws
         return int(ws[off:off + 64].view(torch.int32)[_lib.PVN3D_MS_STAT_CERTIFIED].item())
+
+    def last_counts(self) -> torch.Tensor:
+        """diagnostics: int32 inlier count of every input point of the last call (indexed like pts4)"""
+        ws, off = self._last_ws
+        cap, nf = self._last_cap_nf
+        o = off + int(_lib.load().pvn3d_meanshift_workspace_counts_offset(cap, nf, int(self.max_iter)))
+        return ws[o:o + 4 * cap].view(torch.int32)

@@ -155,11 +155,17 @@ class FramePipeline:
         with torch.cuda.stream(self._copy_stream):
             if self._set_free[turn] is not None:
                 self._copy_stream.wait_event(self._set_free[turn])
-            for key in ("cld_rgb_nrm", "pcld", "labels", "ctr_of", "kp_of"):
+            # the cloud goes first and gets its own event: the look-ahead sampling (4 ms on the critical path of the NEXT
+            # step) needs nothing else, and must not wait for the 45 MB of votes behind it
+            st["cld_rgb_nrm"][:b].copy_(hb["cld_rgb_nrm"], non_blocking=True)
+            cloud_up = torch.cuda.Event()
+            cloud_up.record(self._copy_stream)
+            for key in ("pcld", "labels", "ctr_of", "kp_of"):
                 st[key][:b].copy_(hb[key], non_blocking=True)
             uploaded = torch.cuda.Event()
             uploaded.record(self._copy_stream)
         self._staged[turn] = (id(hb), uploaded)
+        self._cloud_up = cloud_up
         return uploaded
 
     @torch.no_grad()
@@ -188,8 +194,8 @@ class FramePipeline:
         cur.wait_event(uploaded)
         next_cloud = None
         if next_hb is not None and self.overlap and self.fused is not None:
-            up2 = self._upload(next_hb, turn ^ 1)
-            next_cloud = (self._sets[turn ^ 1]["cld_rgb_nrm"][:next_hb["pcld"].shape[0]], up2)
+            self._upload(next_hb, turn ^ 1)
+            next_cloud = (self._sets[turn ^ 1]["cld_rgb_nrm"][:next_hb["pcld"].shape[0]], self._cloud_up)
             self._plan_host = id(next_hb)
         poses, present = self.run_device(st["cld_rgb_nrm"][:b], st["pcld"][:b], st["labels"][:b],
                                          st["ctr_of"][:b], st["kp_of"][:b], next_cloud=next_cloud)

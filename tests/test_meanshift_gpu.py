@@ -126,3 +126,41 @@ def test_multi_tile_fit_and_max_iter_cap(cuda_dev):
 def test_cpu_tensor_is_rejected():
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         MeanShiftTorch(0.08).fit(torch.zeros(4, 3))
+
+
+@pytest.mark.parametrize("kind", ["cluster", "two", "uniform", "coincident", "line", "tiny_bw", "huge_bw", "far_origin"])
+def test_pruned_density_equals_brute_force(cuda_dev, kind):
+    """the exact pass that avoids n^2 tests (radial counting sort + triangle inequality) must give the same inlier
+    count for EVERY input point as the brute-force pass, on vote-like and on adversarial clouds"""
+    rng = np.random.default_rng(len(kind))
+    n, bw = 3000, 0.08
+    if kind == "cluster":
+        A = np.array([0.1, -0.05, 0.8]) + rng.normal(0, 0.005, (n, 3)); A[:300] = rng.uniform([-0.5, -0.4, 0.6], [0.5, 0.4, 1.2], (300, 3))
+    elif kind == "two":
+        A = np.concatenate([np.array([0.0, 0.0, 0.8]) + rng.normal(0, 0.01, (n // 2, 3)), np.array([0.12, 0.0, 0.8]) + rng.normal(0, 0.01, (n // 2, 3))])
+    elif kind == "uniform":
+        A = rng.uniform(-0.3, 0.3, (n, 3))
+    elif kind == "coincident":
+        A = np.tile(np.array([[0.3, 0.2, 0.9]]), (n, 1)); A[::7] += 0.0799999; A[::11] += 0.0800001
+    elif kind == "line":
+        A = np.stack([np.linspace(0, 2.0, n), np.zeros(n), np.ones(n)], 1)       # spacing 0.67 mm: counts change every point
+    elif kind == "tiny_bw":
+        bw = 0.004; A = np.array([0.1, 0.0, 0.7]) + rng.normal(0, 0.005, (n, 3))
+    elif kind == "huge_bw":
+        bw = 5.0; A = rng.uniform(-1, 1, (n, 3))
+    else:
+        A = np.array([120.0, -75.0, 300.0]) + rng.normal(0, 0.03, (n, 3))
+    At = torch.from_numpy(A.astype(np.float32)).to(cuda_dev)
+    out = {}
+    for brute in (False, True):
+        ms = MeanShiftTorch(bw, mode="certified")
+        ms.brute_density = brute
+        ctr, labels = ms.fit(At)
+        out[brute] = (ms.last_counts()[:n].clone(), labels.clone(), ctr.clone())
+    assert torch.equal(out[False][0], out[True][0]), int((out[False][0] != out[True][0]).sum())
+    assert torch.equal(out[False][1], out[True][1])
+    # sanity against a torch restatement on the GPU (its contraction order is not pinned: pairs exactly at the
+    # threshold may differ, nothing else)
+    d = At[:, None, :] - At[None, :, :]
+    want = (torch.sqrt((d * d).sum(-1)) < torch.tensor(bw, dtype=torch.float32, device=cuda_dev)).sum(1).int()
+    assert int((out[True][0] - want).abs().max()) <= 3
