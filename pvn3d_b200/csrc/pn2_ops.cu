@@ -258,6 +258,105 @@ three_nn_kernel(const float *__restrict__ unknown, const float *__restrict__ kno
 }
 
 // ------------------------------------------------------------------------------------------------
+// three_nn through an x-sorted copy of the known set.  The reference cascade (ascending k, strict '<') ends with
+// the three smallest (d2, k) pairs in lexicographic order, so the scan order is free as long as ties are broken by
+// the index.  With the known points of a frame sorted by x, a query walks outward from its own x in both
+// directions and stops when the squared x-gap alone exceeds its third-best distance: d2 = fma(dz,dz, fma(dx,dx,
+// dy*dy)) >= fl(dx*dx) by monotonicity of rounding, so nothing beyond can enter (gaps EQUAL to d3 are still
+// examined: they could tie).  At the FP1 level (12288 queries x 2048 known) a query tests ~130 candidates instead
+// of 2048.  d2 is evaluated by the same expression as the scan, indices / distances stay bit-exact.
+constexpr int kNnSlabMaxM = 4096;
+
+__global__ void __launch_bounds__(512) nn_sort_known_kernel(const float *__restrict__ known, int m, int m_pad,
+                                                            float4 *__restrict__ sorted) {
+  extern __shared__ float4 s_k[];
+  known += static_cast<size_t>(blockIdx.x) * m * 3;
+  sorted += static_cast<size_t>(blockIdx.x) * m_pad;
+  const float inf = __int_as_float(0x7f800000);
+  for (int i = threadIdx.x; i < m_pad; i += blockDim.x)
+    s_k[i] = i < m ? make_float4(__ldg(known + i * 3), __ldg(known + i * 3 + 1), __ldg(known + i * 3 + 2), __int_as_float(i))
+                   : make_float4(inf, inf, inf, __int_as_float(0x7fffffff));
+  __syncthreads();
+  for (int k = 2; k <= m_pad; k <<= 1) {          // bitonic sort by (x, index)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < m_pad; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const float4 a = s_k[i], b = s_k[l];
+          const bool a_gt_b = a.x > b.x || (a.x == b.x && __float_as_int(a.w) > __float_as_int(b.w));
+          if (a_gt_b == ((i & k) == 0)) { s_k[i] = b; s_k[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < m_pad; i += blockDim.x) sorted[i] = s_k[i];
+}
+
+__device__ __forceinline__ void best3_push_lex(Best3 &b, float d, int k) {
+  // insert (d, k) if it precedes the current third pair in (distance, index) order
+  if (d < b.d3 || (d == b.d3 && k < b.i3)) {
+    if (d < b.d1 || (d == b.d1 && k < b.i1)) {
+      b.d3 = b.d2; b.i3 = b.i2;
+      b.d2 = b.d1; b.i2 = b.i1;
+      b.d1 = d;    b.i1 = k;
+    } else if (d < b.d2 || (d == b.d2 && k < b.i2)) {
+      b.d3 = b.d2; b.i3 = b.i2;
+      b.d2 = d;    b.i2 = k;
+    } else {
+      b.d3 = d;    b.i3 = k;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kNnThreads)
+three_nn_slab_kernel(const float *__restrict__ unknown, const float4 *__restrict__ sorted, int n, int m, int m_pad,
+                     float *__restrict__ dist2, int *__restrict__ idx) {
+  extern __shared__ float4 s_k[];
+  const int b = blockIdx.y;
+  sorted += static_cast<size_t>(b) * m_pad;
+  for (int i = threadIdx.x; i < m; i += kNnThreads) s_k[i] = sorted[i];
+  __syncthreads();
+  const int j = blockIdx.x * kNnThreads + threadIdx.x;
+  if (j >= n) return;
+  const float *u = unknown + (static_cast<size_t>(b) * n + j) * 3;
+  const float ux = u[0], uy = u[1], uz = u[2];
+  Best3 best;
+  best3_init(best);
+  best.i1 = best.i2 = best.i3 = 0x7fffffff;   // so that any real pair precedes an empty slot; restored to 0 at the end
+  int lo = 0, hi = m;                          // first position with x >= ux
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (s_k[mid].x < ux) lo = mid + 1; else hi = mid;
+  }
+  int l = lo - 1, r = lo;
+  const float inf = __int_as_float(0x7f800000);
+  float gl = inf, gr = inf;                    // squared x-gap of the next candidate on either side
+  if (l >= 0) { const float dx = ux - s_k[l].x; gl = dx * dx; }
+  if (r < m) { const float dx = ux - s_k[r].x; gr = dx * dx; }
+  while (l >= 0 || r < m) {
+    const bool left = gl <= gr;
+    const float g = left ? gl : gr;
+    if (g > best.d3) break;                    // both sides are farther in x alone than the third best
+    const float4 q = s_k[left ? l : r];
+    best3_push_lex(best, ref_sqdist(ux - q.x, uy - q.y, uz - q.z), __float_as_int(q.w));
+    if (left) {
+      --l;
+      gl = inf;
+      if (l >= 0) { const float dx = ux - s_k[l].x; gl = dx * dx; }
+    } else {
+      ++r;
+      gr = inf;
+      if (r < m) { const float dx = ux - s_k[r].x; gr = dx * dx; }
+    }
+  }
+  float *d = dist2 + (static_cast<size_t>(b) * n + j) * 3;
+  int *o = idx + (static_cast<size_t>(b) * n + j) * 3;
+  d[0] = best.d1; d[1] = best.d2; d[2] = best.d3;
+  o[0] = best.d1 < inf ? best.i1 : 0; o[1] = best.d2 < inf ? best.i2 : 0; o[2] = best.d3 < inf ? best.i3 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 // three_interpolate: out[b,c,j] = sum_t points[b,c,idx[b,j,t]] * w[b,j,t]   (interpolate_gpu.cu:72-101)
 // contraction as in the reference SASS (oracle/_ref build, interpolate_gpu.o):
 //   t = p2*w2 (FMUL); t = fma(p1,w1,t); out = fma(p3,w3,t)  -- the MIDDLE product is the bare multiply
@@ -498,6 +597,35 @@ extern "C" int pvn3d_three_nn(const float *unknown, const float *known, int b, i
   if (b == 0 || n == 0) return PVN3D_OK;
   if (b > 65535) return PVN3D_ERR_UNSUPPORTED;
   dim3 grid(ceil_div(n, kNnThreads), b);
+  static const bool slab_env = [] { const char *e = getenv("PVN3D_NN_SLAB"); return !(e && e[0] == '0'); }();
+  if (slab_env && m >= 512 && m <= kNnSlabMaxM && n >= 2 * m) {
+    // x-sorted copy of the known set (stream-ordered scratch), then the outward walk
+    int m_pad = 1;
+    while (m_pad < m) m_pad <<= 1;
+    const size_t smem = static_cast<size_t>(m_pad) * sizeof(float4);
+    static PerDeviceOnce once;
+    if (once.pending()) {
+      PVN3D_CUDA_TRY(cudaFuncSetAttribute(nn_sort_known_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          kNnSlabMaxM * (int)sizeof(float4)), "nn sort smem attr");
+      PVN3D_CUDA_TRY(cudaFuncSetAttribute(three_nn_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          kNnSlabMaxM * (int)sizeof(float4)), "nn slab smem attr");
+      once.mark();
+    }
+    int rc = keep_async_pool_warm();
+    if (rc != PVN3D_OK) return rc;
+    float4 *sorted = nullptr;
+    PVN3D_CUDA_TRY(cudaMallocAsync(&sorted, static_cast<size_t>(b) * m_pad * sizeof(float4), as_stream(stream)),
+                   "three_nn scratch alloc");
+    nn_sort_known_kernel<<<b, 512, smem, as_stream(stream)>>>(known, m, m_pad, sorted);
+    rc = check_launch("nn_sort_known_kernel");
+    if (rc == PVN3D_OK) {
+      three_nn_slab_kernel<<<grid, kNnThreads, static_cast<size_t>(m) * sizeof(float4), as_stream(stream)>>>(
+          unknown, sorted, n, m, m_pad, dist2, idx);
+      rc = check_launch("three_nn_slab_kernel");
+    }
+    cudaFreeAsync(sorted, as_stream(stream));
+    return rc;
+  }
   three_nn_kernel<<<grid, kNnThreads, 0, as_stream(stream)>>>(unknown, known, n, m, dist2, idx);
   return check_launch("three_nn_kernel");
 }

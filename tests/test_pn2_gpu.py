@@ -163,6 +163,27 @@ def test_three_nn_ties_and_small_m(cuda_dev):
     assert torch.isinf(d2[0, 0, 2]) and int(idx[0, 0, 2]) == 0
 
 
+@pytest.mark.parametrize("m,n", [(600, 2000), (2048, 5000), (4096, 9000), (512, 1024)])
+def test_three_nn_sorted_slab_ties_and_padding(cuda_dev, m, n):
+    """the x-sorted walk (m >= 512) against the oracle's index-order cascade on clouds built to tie: duplicated known
+    points (equal distances -> the LOWER index must win, in all three slots), points sharing x, queries ON known
+    points, m not a power of two (padding of the sort), coordinates on a lattice (many equal squared distances)"""
+    rng = np.random.default_rng(m + n)
+    known = rng.integers(-20, 20, size=(2, m, 3)).astype(np.float32) * 0.01          # lattice -> exact ties everywhere
+    known[:, m // 2:m // 2 + m // 4] = known[:, :m // 4]                              # exact duplicates, higher indices
+    known[1, :, 0] = 0.05                                                             # one frame: all known share x
+    unk = rng.integers(-25, 25, size=(2, n, 3)).astype(np.float32) * 0.01
+    unk[:, :m // 8] = known[:, :m // 8]                                               # queries on known points: d2 = 0 ties
+    d2, idx = _ext.three_nn(t(unk, cuda_dev), t(known, cuda_dev))
+    wd2, widx = pn2.three_nn(unk, known)
+    assert np.array_equal(idx.cpu().numpy(), widx), int((idx.cpu().numpy() != widx).sum())
+    assert np.array_equal(d2.cpu().numpy(), wd2)
+    ref = load_ref_ext()
+    if ref is not None:
+        rd2, ridx = ref.three_nn(t(unk, cuda_dev), t(known, cuda_dev))
+        assert np.array_equal(ridx.cpu().numpy(), widx) and np.array_equal(rd2.cpu().numpy(), wd2)
+
+
 def test_three_nn_interpolate_fused(cuda_dev, clouds):
     """fused FP front end == three_nn -> sqrt -> 1/(d+1e-8) -> normalise -> three_interpolate
     (pointnet2_modules.py:183-190) composed from the separate ops + torch."""
