@@ -570,12 +570,13 @@ def b200_arm(args, json_out):
         rooflines = []
         if fam is not None:
             t_mlp = fam["mlp"]
-            mlp_roof = {"kernel": "mlp_layer_kernel (all shared-MLP launches of one batch: SA 8 scales x 3 layers, FP 4 x 2)",
+            mlp_roof = {"kernel": "mlp_layer_kernel (all shared-MLP launches of one batch: 8 SA scales x (per-point first layer, "
+                                  "gather + second layer, third layer + max-pool), 4 FP modules) + factor tables + final transpose",
                         "on_timed_step": True, "bound": "hbm", "achieved": MLP_IO_BYTES * B / t_mlp / 1e6, "peak": peak,
                         "unit": "GB/s", "frac": MLP_IO_BYTES * B / t_mlp / 1e6 / peak, "peak_kind": peak_kind,
-                        # dram__bytes_read.sum + dram__bytes_write.sum over the 32 launches of one batch, `ncu --set full`
-                        # (profiles/ncu_mlp_r02.md): 2.1x the algorithmic bytes -- the inter-layer activations
-                        "traffic": 6863.8 if (B == 32 and cfg["shape"] == "linemod" and not run.pipe.fused.chain) else None,
+                        # dram__bytes_read.sum + dram__bytes_write.sum over the 33 launches of one batch, `ncu --set full`
+                        # (profiles/ncu_mlp_r02.md): 1.5x the algorithmic bytes -- the second-layer activations
+                        "traffic": 4953.0 if (B == 32 and cfg["shape"] == "linemod" and run.pipe.fused.factor) else None,
                         "traffic_unit": "MB per batch (ncu, profiles/ncu_mlp_r02.md)",
                         "ms_per_batch": t_mlp, "algorithmic_MB_per_batch": MLP_IO_BYTES * B / 1e6,
                         "useful_TFLOPs": MLP_FLOPS * B / t_mlp / 1e9,
