@@ -140,12 +140,19 @@ def reference_sweep_counts():
     return [98, 134, 152, 237, 137, 117, 123, 104, 162], 3348     # the same numbers, should the fixture be absent
 
 
+_THREAD_PROBE = {}
+
+
 def best_thread_count(votes, candidates):
     """torch CPU mean-shift sweeps are memory-bound on [n,n,3] temporaries: more threads are not always
-    faster on a many-core host.  Probe (2 sweeps each) and keep the fastest."""
+    faster on a many-core host.  Probe (3 sweeps each, once per process) and keep the fastest."""
     import torch
     from oracle.meanshift_oracle import MeanShiftOracle
 
+    key = (int(votes.shape[0]), tuple(candidates))
+    if key in _THREAD_PROBE:
+        torch.set_num_threads(_THREAD_PROBE[key][0])
+        return _THREAD_PROBE[key]
     res = {}
     for nt in candidates:
         torch.set_num_threads(nt)
@@ -156,7 +163,8 @@ def best_thread_count(votes, candidates):
         res[nt] = (time.perf_counter() - t0) / 4.0          # 3 sweeps + the density/label pass
     best = min(res, key=res.get)
     torch.set_num_threads(best)
-    return best, {str(k): round(v * 1e3, 1) for k, v in res.items()}
+    _THREAD_PROBE[key] = (best, {str(k): round(v * 1e3, 1) for k, v in res.items()})
+    return _THREAD_PROBE[key]
 
 
 def cpu_path_sample(frame, sd, sweep_budget_s, complete_fit):
