@@ -466,6 +466,26 @@ def roofline_query_group(torch, _ext, dev, B, cloud, peak, peak_kind):
             "algorithmic_MB_per_batch": total_bytes / 1e6, "us_per_batch": total_ms * 1e3, "per_launch": per}
 
 
+def heads_timing(torch, runner, dev):
+    """SURVEY section 8 f3 (not part of the frame metric): DenseFusion + the three heads of PVN3D (pvn3d.py:157-182,
+    245-267) on the layer kernel, random-init modules of this package's layout, random CNN embedding, the batch's
+    PointNet++ features.  198.3 GFLOP per 12288-point frame as the reference executes it."""
+    from pvn3d_b200 import heads as H
+
+    b, n = runner.B, runner.cfg["n_points"]
+    torch.manual_seed(0)
+    mods = H.reference_layout_modules(n_classes=22, n_kps=8)
+    eng = H.FusedHeads(*mods, device=dev)
+    g = torch.Generator().manual_seed(1)
+    rgb_emb = torch.randn(b, 128, n, generator=g).to(dev)
+    cld_emb = runner.pipe.features if runner.pipe.features is not None else torch.randn(b, 128, n, generator=g).abs().to(dev)
+    ms = runner.median_ms(lambda: eng(rgb_emb, cld_emb), reps=3, warm=1)
+    flops = 198.3e9 * b * n / 12288
+    return {"ms_per_batch": ms, "ms_per_frame": ms / b, "nominal_TFLOPs": flops / ms / 1e9,
+            "what": "DenseFusion + SEG/KpOF/CtrOf heads, TF32 tensor cores; conv4 only ever averaged (32-row partial sums in the "
+                    "epilogue), the broadcast global feature folded into a per-frame bias of every head's first layer (K 768 of 1792)"}
+
+
 def stock_gpu_baseline(torch, runner, dev):
     """The unmodified reference on this GPU: reference Python (staged under oracle/_ref/py)
     with its own compiled `_ext` (oracle/_ref/_ext.so): Pointnet2MSG.forward on the whole batch, and
@@ -686,6 +706,8 @@ def b200_arm(args, json_out):
             try:
                 rs = Runner(torch, CONFIGS["linemod"], dev, rank, 1, args.ms_mode, overlap=overlap, n_rot=1)
                 line["stock_gpu_baseline"] = stock_gpu_baseline(torch, rs, dev)
+                rs.step_device(0)
+                line["densefusion_heads"] = heads_timing(torch, rs, dev)
                 del rs
             except Exception as e:           # the stock leg must never take the bench line down
                 line["stock_gpu_baseline"] = {"unavailable": repr(e)[:300]}

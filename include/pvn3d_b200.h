@@ -169,6 +169,17 @@ int pvn3d_three_nn_interpolate(const float *unknown, const float *known, const f
 int pvn3d_mlp_dense(const float *a, int lda, int a_cols, long long rows, const float *w,
                     const float *bias, int k_pad, int n_pad, int flags, int pool, float *out, int ldo,
                     int col0, pvn3d_stream_t stream);
+/* pvn3d_mlp_dense with ONE BIAS VECTOR PER BATCH ELEMENT: bias is [rows / rows_per_frame][n_pad] and row p uses
+ * vector p / rows_per_frame (rows_per_frame % 128 == 0).  Lets a layer whose input contains a per-frame constant
+ * (DenseFusion's broadcast global feature, pvn3d.py:178-182) drop those K columns: W_c . g_b is folded into the bias. */
+int pvn3d_mlp_dense_frame_bias(const float *a, int lda, int a_cols, long long rows, int rows_per_frame,
+                               const float *w, const float *bias, int k_pad, int n_pad, int flags, float *out,
+                               int ldo, int col0, pvn3d_stream_t stream);
+/* out[g, :] = sum over the 32 rows p in [32 g, 32 g + 32) of relu(a[p] . W^T + bias)  -- partial sums of a mean over
+ * points (AvgPool1d of DenseFusion, pvn3d.py:165,178) without storing the per-point activations; out rows = ceil(rows/32).
+ * Summation order is fixed (reproducible). */
+int pvn3d_mlp_dense_sum32(const float *a, int lda, int a_cols, long long rows, const float *w, const float *bias,
+                          int k_pad, int n_pad, int flags, float *out, int ldo, int col0, pvn3d_stream_t stream);
 /* First layer of one SA scale with QueryAndGroup fused into the operand producer: row (b,j,s) =
  * [ feat_pm[b, idx[b,j,s], 0:c_feat] | xyz[b,idx] - new_xyz[b,j] | 0.. ]  -- NOTE the column order:
  * the reference concatenates xyz FIRST (pointnet2_utils.py:319-321); W must have its three xyz

@@ -42,7 +42,7 @@ constexpr int kMlpThreads = (kMlpEpiWarps + kMlpProWarps + 1) * 32;  // warp 12:
 constexpr int kMlpMaxStages = 6;
 
 enum : int { PRO_DENSE = 0, PRO_SA_GATHER = 1, PRO_FP_INTERP = 2, PRO_SA_FACT = 3, PRO_FP_FACT = 4 };
-enum : int { EPI_STORE = 0, EPI_MAXPOOL = 1 };
+enum : int { EPI_STORE = 0, EPI_MAXPOOL = 1, EPI_SUMPOOL = 2 };
 
 struct MlpArgs {
   // W as a TMA tensor map ([n_pad][k_pad] fp32, box 32 columns x bn rows, SWIZZLE_128B): one
@@ -77,6 +77,7 @@ struct MlpArgs {
   int round_out;  // store TF32-rounded values (the next layer then takes them with a_tf32)
   int pool;       // nsample of the max-pool epilogue (8, 16 or 32)
   int reserve_sms;  // host only: SMs left to concurrent kernels (PVN3D_MLP_RESERVE_SMS in flags)
+  int bias_npb;     // > 0: bias is [rows / bias_npb][n_pad] -- one vector per batch element (bias_npb % 128 == 0)
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
@@ -458,6 +459,19 @@ __device__ __forceinline__ void warp_colmax_32(float (&v)[32], unsigned lane) {
     }
   }
 }
+// After the call, lane l holds in v[0] the SUM over the 32 lanes of the ORIGINAL v[l] (fixed order: reproducible).
+__device__ __forceinline__ void warp_colsum_32(float (&v)[32], unsigned lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool hi = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float keep = hi ? v[i + o] : v[i];
+      const float send = hi ? v[i] : v[i + o];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+}
 // groups of 16 lanes: lane l (l' = l & 15) ends with columns 2l', 2l'+1 in v[0], v[1]
 __device__ __forceinline__ void warp_colmax_16(float (&v)[32], unsigned lane) {
 #pragma unroll
@@ -651,18 +665,36 @@ __global__ void __launch_bounds__(kMlpThreads, OCC) mlp_layer_kernel(const __gri
       const long long prow = p0 + warp * 32 + lane;
       const uint32_t stg = ring + static_cast<uint32_t>(S) * stage_bytes + warp * 4096u;  // after the ring
       const uint32_t lane_addr = tmem + buf * static_cast<uint32_t>(a.tmem_cols) + ((warp * 32u) << 16);
+      // per-frame bias (a 128-row tile never straddles batch elements: bias_npb % 128 == 0)
+      const float *bias_t = a.bias + (a.bias_npb > 0 ? (p0 / a.bias_npb) * a.n_pad : 0);
       for (int c0 = 0; c0 < bn; c0 += 32) {
         float v[32];
         const int cw = min(32, bn - c0);
         if (cw == 32) tmem_ld32(lane_addr + c0, v);
         else tmem_ld16(lane_addr + c0, v);
-        if (EPI == EPI_STORE) {
+        if (EPI == EPI_SUMPOOL) {
+          // sum over the 32 rows of the warp of relu(acc + bias): partial sums of a mean over points
+          // (DenseFusion's AvgPool1d, pvn3d.py:165,178); rows past the end contribute 0
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 bq = q * 4 < cw ? ldg128(bias_t + n0 + c0 + q * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool on = prow < a.rows && q * 4 < cw;
+            v[q * 4 + 0] = on ? fmaxf(v[q * 4 + 0] + bq.x, 0.f) : 0.f;
+            v[q * 4 + 1] = on ? fmaxf(v[q * 4 + 1] + bq.y, 0.f) : 0.f;
+            v[q * 4 + 2] = on ? fmaxf(v[q * 4 + 2] + bq.z, 0.f) : 0.f;
+            v[q * 4 + 3] = on ? fmaxf(v[q * 4 + 3] + bq.w, 0.f) : 0.f;
+          }
+          warp_colsum_32(v, lane);
+          const int col = static_cast<int>(lane);
+          if (col < cw && p0 + warp * 32 < a.rows)
+            a.out[((p0 + warp * 32) / 32) * a.ldo + a.col0 + n0 + c0 + col] = v[0];
+        } else if (EPI == EPI_STORE) {
           // bias / ReLU / rounding on the thread's own row, then through a swizzled 4 KB staging tile
           // so that the global stores are 128-byte row segments (8 lanes per row, 4 rows per STG.128)
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             if (q * 4 < cw) {
-              const float4 bq = ldg128(a.bias + n0 + c0 + q * 4);
+              const float4 bq = ldg128(bias_t + n0 + c0 + q * 4);
               float4 r;
               r.x = v[q * 4 + 0] + bq.x;
               r.y = v[q * 4 + 1] + bq.y;
@@ -702,7 +734,7 @@ __global__ void __launch_bounds__(kMlpThreads, OCC) mlp_layer_kernel(const __gri
             warp_colmax_32(v, lane);
             const int col = static_cast<int>(lane);
             if (col < cw && p0 + warp * 32 < a.rows) {
-              float r = v[0] + __ldg(a.bias + n0 + c0 + col);
+              float r = v[0] + __ldg(bias_t + n0 + c0 + col);
               if (a.relu) r = fmaxf(r, 0.f);
               if (a.round_out) r = to_tf32(r);
               a.out[grow0 * a.ldo + a.col0 + n0 + c0 + col] = r;
@@ -712,8 +744,8 @@ __global__ void __launch_bounds__(kMlpThreads, OCC) mlp_layer_kernel(const __gri
             const int g = lane >> 4, col = static_cast<int>(lane & 15u) * 2;
             if (col < cw && p0 + warp * 32 + g * 16 < a.rows) {
               float2 r;
-              r.x = v[0] + __ldg(a.bias + n0 + c0 + col);
-              r.y = v[1] + __ldg(a.bias + n0 + c0 + col + 1);
+              r.x = v[0] + __ldg(bias_t + n0 + c0 + col);
+              r.y = v[1] + __ldg(bias_t + n0 + c0 + col + 1);
               if (a.relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); }
               if (a.round_out) { r.x = to_tf32(r.x); r.y = to_tf32(r.y); }
               *reinterpret_cast<float2 *>(a.out + (grow0 + g) * a.ldo + a.col0 + n0 + c0 + col) = r;
@@ -723,10 +755,10 @@ __global__ void __launch_bounds__(kMlpThreads, OCC) mlp_layer_kernel(const __gri
             const int g = lane >> 3, col = static_cast<int>(lane & 7u) * 4;
             if (col < cw && p0 + warp * 32 + g * 8 < a.rows) {
               float4 r;
-              r.x = v[0] + __ldg(a.bias + n0 + c0 + col);
-              r.y = v[1] + __ldg(a.bias + n0 + c0 + col + 1);
-              r.z = v[2] + __ldg(a.bias + n0 + c0 + col + 2);
-              r.w = v[3] + __ldg(a.bias + n0 + c0 + col + 3);
+              r.x = v[0] + __ldg(bias_t + n0 + c0 + col);
+              r.y = v[1] + __ldg(bias_t + n0 + c0 + col + 1);
+              r.z = v[2] + __ldg(bias_t + n0 + c0 + col + 2);
+              r.w = v[3] + __ldg(bias_t + n0 + c0 + col + 3);
               if (a.relu) {
                 r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
               }
@@ -1583,4 +1615,37 @@ extern "C" int pvn3d_mlp_fp_fact(const float *p, const float *s, int ld, int c_v
   a.relu = flags & PVN3D_MLP_RELU; a.round_out = (flags & PVN3D_MLP_ROUND_OUT) ? 1 : 0;
   a.reserve_sms = (flags >> 8) & 0xff;
   return dispatch(a, PRO_FP_FACT, 0, as_stream(stream));
+}
+
+extern "C" int pvn3d_mlp_dense_frame_bias(const float *a, int lda, int a_cols, long long rows, int rows_per_frame,
+                                          const float *w, const float *bias, int k_pad, int n_pad, int flags,
+                                          float *out, int ldo, int col0, pvn3d_stream_t stream) {
+  if (!a || !w || !bias || !out || lda < a_cols || a_cols < 0 || a_cols % 4 || rows < 0 || ldo % 4 || col0 % 4 ||
+      rows_per_frame <= 0 || rows_per_frame % kMlpBM || rows % rows_per_frame)
+    return PVN3D_ERR_INVALID_ARG;
+  MlpArgs m{};
+  m.w = w; m.bias = bias; m.rows = rows; m.k_pad = k_pad; m.n_pad = n_pad;
+  m.a = a; m.lda = lda; m.a_cols = a_cols;
+  m.out = out; m.ldo = ldo; m.col0 = col0;
+  m.relu = flags & PVN3D_MLP_RELU; m.round_out = (flags & PVN3D_MLP_ROUND_OUT) ? 1 : 0;
+  m.a_tf32 = (flags & PVN3D_MLP_A_TF32) ? 1 : 0;
+  m.reserve_sms = (flags >> 8) & 0xff;
+  m.bias_npb = rows_per_frame;
+  return dispatch(m, PRO_DENSE, 0, as_stream(stream));
+}
+
+extern "C" int pvn3d_mlp_dense_sum32(const float *a, int lda, int a_cols, long long rows, const float *w,
+                                     const float *bias, int k_pad, int n_pad, int flags, float *out, int ldo,
+                                     int col0, pvn3d_stream_t stream) {
+  if (!a || !w || !bias || !out || lda < a_cols || a_cols < 0 || a_cols % 4 || rows < 0 || ldo % 4 || col0 % 4)
+    return PVN3D_ERR_INVALID_ARG;
+  MlpArgs m{};
+  m.w = w; m.bias = bias; m.rows = rows; m.k_pad = k_pad; m.n_pad = n_pad;
+  m.a = a; m.lda = lda; m.a_cols = a_cols;
+  m.out = out; m.ldo = ldo; m.col0 = col0;
+  m.relu = 1;
+  m.a_tf32 = (flags & PVN3D_MLP_A_TF32) ? 1 : 0;
+  m.reserve_sms = (flags >> 8) & 0xff;
+  m.pool = 32;
+  return launch_mlp<PRO_DENSE, EPI_SUMPOOL>(m, as_stream(stream));
 }
