@@ -246,8 +246,8 @@ __global__ void __launch_bounds__(kMsThreads) ms_density_kernel(MsArgs a) {
 struct MsPruneSmem {
   float4 pts[kMsPruneMax];        // original order: x, y, z, r
   int idx_sorted[kMsPruneMax];    // point indices in order of increasing radius
-  int cursor[kMsPruneBins];       // scatter cursors of the counting sort
-  int bin_start[kMsPruneBins + 1];
+  int cursor[kMsPruneBins + 1];   // scatter cursors of the counting sort (+ overflow bin)
+  int bin_start[kMsPruneBins + 2];   // [kMsPruneBins] = first point of the overflow bin (non-finite coordinates)
   float red[kMsWarps][4];
   float4 pivot;
   float max_r;
@@ -288,13 +288,15 @@ __global__ void __launch_bounds__(kMsThreads, 2) ms_density_pruned_kernel(MsArgs
 
   // ---- points into shared memory, pivot = robust centre ------------------------------------------------
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  // (points with a NaN / inf coordinate never count and are never counted in the brute-force pass -- every
+  // distance to them is NaN or inf; here they are kept out of the pivot and parked in an overflow bin)
   for (int i = t; i < n; i += kMsThreads) {
     const float4 p = a.pts[start + i];
     sm.pts[i] = make_float4(p.x, p.y, p.z, 0.f);
-    acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += 1.f;
+    if (fabsf(p.x) + fabsf(p.y) + fabsf(p.z) < __int_as_float(0x7f800000)) { acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += 1.f; }
   }
   float4 sum = ms_block_sum4(sm, acc);
-  float3 c = make_float3(sum.x / sum.w, sum.y / sum.w, sum.z / sum.w);
+  float3 c = sum.w > 0.f ? make_float3(sum.x / sum.w, sum.y / sum.w, sum.z / sum.w) : make_float3(0.f, 0.f, 0.f);
 #pragma unroll 1
   for (int round = 0; round < 2; ++round) {
     const float rad = round == 0 ? 2.f * bw : bw;
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(kMsThreads, 2) ms_density_pruned_kernel(MsArgs
     for (int i = t; i < n; i += kMsThreads) {
       const float4 p = sm.pts[i];
       const float dx = p.x - c.x, dy = p.y - c.y, dz = p.z - c.z;
-      if (dx * dx + dy * dy + dz * dz < rad * rad) { acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += 1.f; }
+      if (dx * dx + dy * dy + dz * dz < rad * rad) { acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += 1.f; }   // false for NaN
     }
     sum = ms_block_sum4(sm, acc);
     if (sum.w > 0.f) c = make_float3(sum.x / sum.w, sum.y / sum.w, sum.z / sum.w);
@@ -315,13 +317,13 @@ __global__ void __launch_bounds__(kMsThreads, 2) ms_density_pruned_kernel(MsArgs
     const float dx = p.x - c.x, dy = p.y - c.y, dz = p.z - c.z;
     p.w = sqrtf(dx * dx + dy * dy + dz * dz);
     sm.pts[i] = p;
-    rmax = fmaxf(rmax, p.w);
+    if (p.w < __int_as_float(0x7f800000)) rmax = fmaxf(rmax, p.w);   // finite radii only
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
   __syncthreads();
   if ((t & 31) == 0) sm.red[t >> 5][0] = rmax;
-  for (int b = t; b <= kMsPruneBins; b += kMsThreads) sm.bin_start[b] = 0;
+  for (int b = t; b <= kMsPruneBins + 1; b += kMsThreads) sm.bin_start[b] = 0;
   __syncthreads();
   rmax = sm.red[0][0];
 #pragma unroll
@@ -332,7 +334,8 @@ __global__ void __launch_bounds__(kMsThreads, 2) ms_density_pruned_kernel(MsArgs
     const float x = r * inv_w;   // may be huge when every point coincides (rmax = 0): clamp before the conversion
     return x >= static_cast<float>(kMsPruneBins - 1) ? kMsPruneBins - 1 : max(0, static_cast<int>(x));
   };
-  for (int i = t; i < n; i += kMsThreads) atomicAdd(&sm.bin_start[bin_of(sm.pts[i].w) + 1], 1);   // histogram, shifted by one
+  auto bin_of_point = [&](float r) { return r < __int_as_float(0x7f800000) ? bin_of(r) : kMsPruneBins; };   // overflow bin
+  for (int i = t; i < n; i += kMsThreads) atomicAdd(&sm.bin_start[bin_of_point(sm.pts[i].w) + 1], 1);   // histogram, shifted by one
   __syncthreads();
   {  // inclusive scan of the shifted histogram = exclusive bin starts; 8 bins per thread
     constexpr int per = kMsPruneBins / kMsThreads;
@@ -356,12 +359,15 @@ __global__ void __launch_bounds__(kMsThreads, 2) ms_density_pruned_kernel(MsArgs
     for (int q = 0; q < per; ++q) sm.bin_start[1 + t * per + q] = base + local[q];
   }
   __syncthreads();
+  if (t == 0) sm.bin_start[kMsPruneBins + 1] += sm.bin_start[kMsPruneBins];   // overflow bin: [n_finite, n)
+  __syncthreads();
+  const int n_fin = sm.bin_start[kMsPruneBins];   // finite points come first in the sorted order
   // scatter: cursor per bin = its start (kept in r_sorted's storage as ints until the points land)
   int *cursor = sm.cursor;
-  for (int b = t; b < kMsPruneBins; b += kMsThreads) cursor[b] = sm.bin_start[b];
+  for (int b = t; b <= kMsPruneBins; b += kMsThreads) cursor[b] = sm.bin_start[b];
   __syncthreads();
   for (int i = t; i < n; i += kMsThreads) {
-    const int pos = atomicAdd(&cursor[bin_of(sm.pts[i].w)], 1);
+    const int pos = atomicAdd(&cursor[bin_of_point(sm.pts[i].w)], 1);
     sm.idx_sorted[pos] = i;
   }
   __syncthreads();
@@ -374,13 +380,15 @@ __global__ void __launch_bounds__(kMsThreads, 2) ms_density_pruned_kernel(MsArgs
     const float4 me = sm.pts[i];
     const float lo = bw_lo - me.w, hi = me.w + bw_hi;
     int count = 0, first = 0;
-    if (lo > 0.f) {
+    if (q >= n_fin) {
+      first = n_fin;                           // non-finite point: empty band, count 0 (as every test on it fails)
+    } else if (lo > 0.f) {
       first = sm.bin_start[bin_of(lo)];       // every point of an earlier bin has r_j < lo: certainly within bw of i
       count = first;
     } else {
       first = sm.bin_start[bin_of(fmaxf(me.w - bw_hi, 0.f))];   // earlier bins: r_j < r_i - bw - eps, certainly outside
     }
-    const int last = hi * inv_w >= static_cast<float>(kMsPruneBins) ? n : sm.bin_start[bin_of(hi) + 1];
+    const int last = q >= n_fin ? n_fin : (hi * inv_w >= static_cast<float>(kMsPruneBins) ? n_fin : sm.bin_start[bin_of(hi) + 1]);
     for (int pos = first; pos < last; ++pos) {
       const float4 p = sm.pts[sm.idx_sorted[pos]];
       // dis = torch.norm(Ar - Cr): diff = A_j - A_i, exactly as the brute-force pass

@@ -128,7 +128,7 @@ def test_cpu_tensor_is_rejected():
         MeanShiftTorch(0.08).fit(torch.zeros(4, 3))
 
 
-@pytest.mark.parametrize("kind", ["cluster", "two", "uniform", "coincident", "line", "tiny_bw", "huge_bw", "far_origin"])
+@pytest.mark.parametrize("kind", ["cluster", "two", "uniform", "coincident", "line", "tiny_bw", "huge_bw", "far_origin", "nan_inf"])
 def test_pruned_density_equals_brute_force(cuda_dev, kind):
     """the exact pass that avoids n^2 tests (radial counting sort + triangle inequality) must give the same inlier
     count for EVERY input point as the brute-force pass, on vote-like and on adversarial clouds"""
@@ -148,6 +148,11 @@ def test_pruned_density_equals_brute_force(cuda_dev, kind):
         bw = 0.004; A = np.array([0.1, 0.0, 0.7]) + rng.normal(0, 0.005, (n, 3))
     elif kind == "huge_bw":
         bw = 5.0; A = rng.uniform(-1, 1, (n, 3))
+    elif kind == "nan_inf":       # non-finite votes never count and are never counted (every test on them fails)
+        A = np.array([0.1, -0.05, 0.8]) + rng.normal(0, 0.01, (n, 3))
+        A[rng.choice(n, 7, replace=False)] = np.nan
+        A[rng.choice(n, 5, replace=False), 1] = np.inf
+        A[17, 2] = -np.inf
     else:
         A = np.array([120.0, -75.0, 300.0]) + rng.normal(0, 0.03, (n, 3))
     At = torch.from_numpy(A.astype(np.float32)).to(cuda_dev)
@@ -164,3 +169,6 @@ def test_pruned_density_equals_brute_force(cuda_dev, kind):
     d = At[:, None, :] - At[None, :, :]
     want = (torch.sqrt((d * d).sum(-1)) < torch.tensor(bw, dtype=torch.float32, device=cuda_dev)).sum(1).int()
     assert int((out[True][0] - want).abs().max()) <= 3
+    if kind == "nan_inf":
+        bad = ~torch.isfinite(At).all(1)
+        assert int(out[False][0][bad].abs().max()) == 0 and not bool(out[False][1][bad].any())
