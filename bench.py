@@ -296,8 +296,7 @@ class Runner:
                                        first_frame=rank * B, **kw)
         self.pipe = FramePipeline(cfg["shape"], B, n_points=cfg["n_points"], device=dev, lm_obj_id=1, ms_mode=ms_mode,
                                   engine=engine, overlap=overlap, bandwidth=bandwidth,
-                                  pose_stream=os.environ.get("PVN3D_POSE_STREAM", "1") != "0",
-                                  fps_chunk=int(os.environ.get("PVN3D_FPS_CHUNK", "16")))
+                                  pose_stream=os.environ.get("PVN3D_POSE_STREAM", "1") != "0")
         host = synth.stack(self.frames)
         self.n_rot = n_rot
         self.host_rot = [FramePipeline.pin_batch({k: np.roll(v, (B // n_rot) * r, axis=0) for k, v in host.items()})
@@ -599,13 +598,13 @@ def b200_arm(args, json_out):
         if fam is not None:
             t_mlp = fam["mlp"]
             mlp_roof = {"kernel": "mlp_layer_kernel (all shared-MLP launches of one batch: 8 SA scales x (per-point first layer, "
-                                  "gather + second layer, third layer + max-pool), 4 FP modules) + factor tables + final transpose",
+                                  "gather + second layer, third layer + max-pool), 4 FP modules, the last one storing [B,128,N] directly) + factor tables",
                         "on_timed_step": True, "bound": "hbm", "achieved": MLP_IO_BYTES * B / t_mlp / 1e6, "peak": peak,
                         "unit": "GB/s", "frac": MLP_IO_BYTES * B / t_mlp / 1e6 / peak, "peak_kind": peak_kind,
                         # dram__bytes_read.sum + dram__bytes_write.sum over the 33 launches of one batch, `ncu --set full`
-                        # (profiles/ncu_mlp_r02.md): 1.5x the algorithmic bytes -- the second-layer activations
-                        "traffic": 4953.0 if (B == 32 and cfg["shape"] == "linemod" and run.pipe.fused.factor) else None,
-                        "traffic_unit": "MB per batch (ncu, profiles/ncu_mlp_r02.md)",
+                        # (profiles/ncu_mlp_r02c.md): 1.5x the algorithmic bytes -- the second-layer activations
+                        "traffic": 4964.1 if (B == 32 and cfg["shape"] == "linemod" and run.pipe.fused.factor) else None,
+                        "traffic_unit": "MB per batch (ncu, profiles/ncu_mlp_r02c.md)",
                         "ms_per_batch": t_mlp, "algorithmic_MB_per_batch": MLP_IO_BYTES * B / 1e6,
                         "useful_TFLOPs": MLP_FLOPS * B / t_mlp / 1e9,
                         "note": "algorithmic bytes = SURVEY 8d MLP stage I/O with every SharedMLP(+max-pool) fused (100.2 MB/frame); "
@@ -619,7 +618,7 @@ def b200_arm(args, json_out):
                               "bound": "issue", "ms_per_batch": fam["ball"]})
             rooflines.append({"kernel": "three_nn_kernel + nn_weights_kernel (4 levels)", "on_timed_step": True,
                               "bound": "issue", "ms_per_batch": fam["three_nn"]})
-            rooflines.append({"kernel": "glue (new_xyz gather, final [B,N,128]->[B,128,N] transpose)", "on_timed_step": True,
+            rooflines.append({"kernel": "glue (xyz split, new_xyz gathers)", "on_timed_step": True,
                               "ms_per_batch": fam["glue"]})
             line["roofline"] = mlp_roof
         # mean-shift: pair evaluations per second against the MUFU bound

@@ -161,6 +161,9 @@ int pvn3d_three_nn_interpolate(const float *unknown, const float *known, const f
 #define PVN3D_MLP_RELU 1
 #define PVN3D_MLP_ROUND_OUT 2
 #define PVN3D_MLP_A_TF32 4
+#define PVN3D_MLP_OUT_CN 16   /* pvn3d_mlp_fp_fact only: out is [b][n_pad][n_unknown] -- the channel-major [B, C, N] layout
+                                 Pointnet2MSG.forward returns (pvn3d.py:154) -- written straight from the accumulator;
+                                 n_pad 128 or 256, n_unknown % 32 == 0, ldo / col0 ignored (else PVN3D_ERR_UNSUPPORTED) */
 /* leave n SMs (0..255) to kernels running concurrently on other streams: the persistent grid is
  * sm_count - n CTAs instead of one per SM (a persistent CTA that cannot be placed stalls its kernel) */
 #define PVN3D_MLP_RESERVE_SMS(n) (((n) & 0xff) << 8)

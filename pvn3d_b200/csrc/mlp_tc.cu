@@ -42,7 +42,7 @@ constexpr int kMlpThreads = (kMlpEpiWarps + kMlpProWarps + 1) * 32;  // warp 12:
 constexpr int kMlpMaxStages = 6;
 
 enum : int { PRO_DENSE = 0, PRO_SA_GATHER = 1, PRO_FP_INTERP = 2, PRO_SA_FACT = 3, PRO_FP_FACT = 4 };
-enum : int { EPI_STORE = 0, EPI_MAXPOOL = 1, EPI_SUMPOOL = 2 };
+enum : int { EPI_STORE = 0, EPI_MAXPOOL = 1, EPI_SUMPOOL = 2, EPI_MAXPOOL_T = 3, EPI_STORE_T = 4 };
 
 struct MlpArgs {
   // W as a TMA tensor map ([n_pad][k_pad] fp32, box 32 columns x bn rows, SWIZZLE_128B): one
@@ -57,7 +57,9 @@ struct MlpArgs {
   int n_pad;          // multiple of 16
   int bn;             // columns per tile (multiple of 16, <= 256)
   int stages;
-  int tmem_cols;      // power of two >= max(32, bn); two accumulators are allocated
+  int tmem_cols;      // power of two >= max(32, bn); acc_bufs accumulators are allocated
+  int acc_bufs;       // 2: the epilogue of tile j overlaps the MMAs of tile j+1; 1: wide tiles (tmem_cols = 256) of two
+                      // co-resident CTAs -- the other CTA's MMAs fill the gap
   // DENSE
   const float *a;
   int lda;
@@ -78,6 +80,7 @@ struct MlpArgs {
   int pool;       // nsample of the max-pool epilogue (8, 16 or 32)
   int reserve_sms;  // host only: SMs left to concurrent kernels (PVN3D_MLP_RESERVE_SMS in flags)
   int bias_npb;     // > 0: bias is [rows / bias_npb][n_pad] -- one vector per batch element (bias_npb % 128 == 0)
+  int out_cn;       // STORE_T: points per frame; out is [rows / out_cn][n_pad][out_cn] (channel-major frames, out_cn % 32 == 0)
 };
 
 // ---- PTX wrappers --------------------------------------------------------------------------------
@@ -519,13 +522,16 @@ struct MlpSmemCtl {
 // two accumulators of <= 128 TMEM columns each) double the loads in flight for the narrow layers.
 template <int PRO, int EPI, int OCC>
 __global__ void __launch_bounds__(kMlpThreads, OCC) mlp_layer_kernel(const __grid_constant__ MlpArgs a) {
-  extern __shared__ unsigned char mlp_smem_raw[];
-  __shared__ MlpSmemCtl ctl;
-  // 1024-byte aligned operand ring (SWIZZLE_128B atoms are 8 rows x 128 B)
-  const uint32_t raw = smem_u32(mlp_smem_raw);
-  const uint32_t ring = (raw + 1023u) & ~1023u;
+  // dynamic shared memory only, 1024-byte aligned: [operand ring: stages x stage_bytes][epilogue staging 4 x 4 KB]
+  // [barriers].  No static block and no alignment slack: two CTAs with 96 KB rings each fit one SM's 228 KB.
+  extern __shared__ __align__(1024) unsigned char mlp_smem_al[];
+  const uint32_t ring = smem_u32(mlp_smem_al);   // SWIZZLE_128B atoms are 8 rows x 128 B
+  if (ring & 1023u) __trap();
   const uint32_t a_bytes = kMlpBM * 128u;
   const uint32_t stage_bytes = a_bytes + ((static_cast<uint32_t>(a.bn) * 128u + 1023u) & ~1023u);
+  MlpSmemCtl &ctl = *reinterpret_cast<MlpSmemCtl *>(mlp_smem_al + static_cast<size_t>(a.stages) * stage_bytes +
+                                                    kMlpEpiWarps * 4096);
+  const unsigned nbuf = static_cast<unsigned>(a.acc_bufs);
 
   const int t = threadIdx.x;
   const unsigned warp = t >> 5, lane = t & 31u;
@@ -550,7 +556,7 @@ __global__ void __launch_bounds__(kMlpThreads, OCC) mlp_layer_kernel(const __gri
     __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(&ctl.tmem_base)),
-                 "r"(static_cast<uint32_t>(2 * a.tmem_cols))
+                 "r"(nbuf * static_cast<uint32_t>(a.tmem_cols))
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -659,8 +665,8 @@ __global__ void __launch_bounds__(kMlpThreads, OCC) mlp_layer_kernel(const __gri
       const long long p0 = rt * kMlpBM;
       const int n0 = nb * a.bn;
       const int bn = min(a.bn, a.n_pad - n0);
-      const unsigned buf = static_cast<unsigned>(j & 1);
-      mbar_wait(&ctl.acc_full[buf], static_cast<unsigned>((j >> 1) & 1));
+      const unsigned buf = nbuf == 2 ? static_cast<unsigned>(j & 1) : 0u;
+      mbar_wait(&ctl.acc_full[buf], static_cast<unsigned>((nbuf == 2 ? (j >> 1) : j) & 1));
       tc_fence_after();
       const long long prow = p0 + warp * 32 + lane;
       const uint32_t stg = ring + static_cast<uint32_t>(S) * stage_bytes + warp * 4096u;  // after the ring
@@ -670,6 +676,12 @@ __global__ void __launch_bounds__(kMlpThreads, OCC) mlp_layer_kernel(const __gri
       for (int c0 = 0; c0 < bn; c0 += 32) {
         float v[32];
         const int cw = min(32, bn - c0);
+        const unsigned chunk = lane & 7u;                       // STORE: the lane's group of four columns
+        const bool col_on = static_cast<int>(chunk) * 4 < cw;
+        float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (EPI == EPI_STORE && col_on) bq = ldg128(bias_t + n0 + c0 + chunk * 4);
+        float bch = 0.f;   // MAXPOOL_T: the lane's channel = n0 + 128 * (c0 / 128) + 32 * warp + lane
+        if (EPI == EPI_MAXPOOL_T || EPI == EPI_STORE_T) bch = __ldg(bias_t + n0 + (c0 & ~127) + warp * 32 + lane);
         if (cw == 32) tmem_ld32(lane_addr + c0, v);
         else tmem_ld16(lane_addr + c0, v);
         if (EPI == EPI_SUMPOOL) {
@@ -688,39 +700,128 @@ __global__ void __launch_bounds__(kMlpThreads, OCC) mlp_layer_kernel(const __gri
           const int col = static_cast<int>(lane);
           if (col < cw && p0 + warp * 32 < a.rows)
             a.out[((p0 + warp * 32) / 32) * a.ldo + a.col0 + n0 + c0 + col] = v[0];
-        } else if (EPI == EPI_STORE) {
-          // bias / ReLU / rounding on the thread's own row, then through a swizzled 4 KB staging tile
-          // so that the global stores are 128-byte row segments (8 lanes per row, 4 rows per STG.128)
+        } else if (EPI == EPI_STORE_T) {
+          // TRANSPOSED accumulator, stored channel-major: lane = channel, registers = 32 consecutive points of one
+          // frame = 128 contiguous bytes of out[frame][channel][:] -- the [B, C, N] layout Pointnet2MSG.forward returns
+          // (pvn3d.py:154) without a transposing pass over the [B*N, C] rows.  Bias / ReLU on the lane's channel, then
+          // through the swizzled staging tile (row = channel) so that one STG.128 writes four full 128-byte lines
+          // (direct stores -- 32 half sectors per instruction -- cost the gathering producers 64 us of LSU time)
+          const long long prow0 = p0 + (c0 & 127);
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
-            if (q * 4 < cw) {
-              const float4 bq = ldg128(bias_t + n0 + c0 + q * 4);
-              float4 r;
-              r.x = v[q * 4 + 0] + bq.x;
-              r.y = v[q * 4 + 1] + bq.y;
-              r.z = v[q * 4 + 2] + bq.z;
-              r.w = v[q * 4 + 3] + bq.w;
-              if (a.relu) {
-                r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
-              }
-              if (a.round_out) {
-                r.x = to_tf32(r.x); r.y = to_tf32(r.y); r.z = to_tf32(r.z); r.w = to_tf32(r.w);
-              }
-              sts128(stg + lane * 128u + ((static_cast<uint32_t>(q) ^ (lane & 7u)) << 4), r.x, r.y, r.z, r.w);
+            float4 r = make_float4(v[q * 4 + 0] + bch, v[q * 4 + 1] + bch, v[q * 4 + 2] + bch, v[q * 4 + 3] + bch);
+            if (a.relu) {
+              r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
             }
+            if (a.round_out) {
+              r.x = to_tf32(r.x); r.y = to_tf32(r.y); r.z = to_tf32(r.z); r.w = to_tf32(r.w);
+            }
+            sts128(stg + lane * 128u + ((static_cast<uint32_t>(q) ^ (lane & 7u)) << 4), r.x, r.y, r.z, r.w);
           }
           __syncwarp();
-          const unsigned chunk = lane & 7u;
-          if (static_cast<int>(chunk) * 4 < cw) {
+          if (prow0 < a.rows) {
+            const long long fb = prow0 / a.out_cn;
+            const long long pt = prow0 - fb * a.out_cn;
+            const int ch0 = n0 + (c0 & ~127) + static_cast<int>(warp * 32 + (lane >> 3));
+            float *o = a.out + (fb * a.n_pad + ch0) * a.out_cn + pt + chunk * 4;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const unsigned row = 4u * i + (lane >> 3);
-              const long long pr = p0 + warp * 32 + row;
-              if (pr < a.rows) {
-                const float4 r = lds128(stg + row * 128u + ((chunk ^ (row & 7u)) << 4));
-                *reinterpret_cast<float4 *>(a.out + pr * a.ldo + a.col0 + n0 + c0 + chunk * 4) = r;
+              const float4 r = lds128(stg + row * 128u + ((chunk ^ (row & 7u)) << 4));
+              *reinterpret_cast<float4 *>(o + static_cast<size_t>(4 * i) * a.out_cn) = r;
+            }
+          }
+          __syncwarp();
+        } else if (EPI == EPI_MAXPOOL_T) {
+          // TRANSPOSED accumulator (the MMA ran as W . A^T): TMEM lane = output channel, column = row of the tile, so
+          // the max over the `pool` consecutive rows of a centre is a max over REGISTERS of one thread -- no
+          // shuffles -- and the 32 lanes of a warp store 32 consecutive channels of one pooled row (128 bytes).
+          // Groups never straddle the end: rows % pool == 0 and 128 % pool == 0.
+          const long long prow0 = p0 + (c0 & 127);          // row of register 0
+          float *o = a.out + a.col0 + n0 + (c0 & ~127) + warp * 32 + lane;
+          if (a.pool == 32) {
+#pragma unroll
+            for (int w = 16; w >= 1; w >>= 1)
+#pragma unroll
+              for (int i = 0; i < w; ++i) v[i] = fmaxf(v[i], v[i + w]);
+            if (prow0 < a.rows) {
+              float r = v[0] + bch;
+              if (a.relu) r = fmaxf(r, 0.f);
+              if (a.round_out) r = to_tf32(r);
+              o[(prow0 >> 5) * a.ldo] = r;
+            }
+          } else if (a.pool == 16) {
+#pragma unroll
+            for (int w = 8; w >= 1; w >>= 1)
+#pragma unroll
+              for (int i = 0; i < w; ++i) {
+                v[i] = fmaxf(v[i], v[i + w]);
+                v[16 + i] = fmaxf(v[16 + i], v[16 + i + w]);
+              }
+#pragma unroll
+            for (int g = 0; g < 2; ++g)
+              if (prow0 + 16 * g < a.rows) {
+                float r = v[16 * g] + bch;
+                if (a.relu) r = fmaxf(r, 0.f);
+                if (a.round_out) r = to_tf32(r);
+                o[((prow0 >> 4) + g) * a.ldo] = r;
+              }
+          } else {  // pool == 8
+#pragma unroll
+            for (int w = 4; w >= 1; w >>= 1)
+#pragma unroll
+              for (int i = 0; i < w; ++i)
+#pragma unroll
+                for (int g = 0; g < 4; ++g) v[8 * g + i] = fmaxf(v[8 * g + i], v[8 * g + i + w]);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              if (prow0 + 8 * g < a.rows) {
+                float r = v[8 * g] + bch;
+                if (a.relu) r = fmaxf(r, 0.f);
+                if (a.round_out) r = to_tf32(r);
+                o[((prow0 >> 3) + g) * a.ldo] = r;
+              }
+          }
+        } else if (EPI == EPI_STORE) {
+          // raw accumulators through a swizzled 4 KB staging tile (thread = row going in, 8 lanes per row coming
+          // out: the global stores are 128-byte row segments, 4 rows per STG.128); bias / ReLU / rounding on the
+          // way out, where a lane keeps ONE group of four columns -- its bias is a single float4 (loaded before
+          // the accumulator wait) and the eight rows it stores are independent instruction streams
+          if (cw == 32) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              sts128(stg + lane * 128u + ((static_cast<uint32_t>(q) ^ (lane & 7u)) << 4), v[q * 4 + 0], v[q * 4 + 1],
+                     v[q * 4 + 2], v[q * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              sts128(stg + lane * 128u + ((static_cast<uint32_t>(q) ^ (lane & 7u)) << 4), v[q * 4 + 0], v[q * 4 + 1],
+                     v[q * 4 + 2], v[q * 4 + 3]);
+          }
+          __syncwarp();
+          if (col_on) {
+            const bool full = p0 + kMlpBM <= a.rows;
+            float4 r[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const unsigned row = 4u * i + (lane >> 3);
+              r[i] = lds128(stg + row * 128u + ((chunk ^ (row & 7u)) << 4));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              r[i].x += bq.x; r[i].y += bq.y; r[i].z += bq.z; r[i].w += bq.w;
+              if (a.relu) {
+                r[i].x = fmaxf(r[i].x, 0.f); r[i].y = fmaxf(r[i].y, 0.f); r[i].z = fmaxf(r[i].z, 0.f); r[i].w = fmaxf(r[i].w, 0.f);
+              }
+              if (a.round_out) {
+                r[i].x = to_tf32(r[i].x); r[i].y = to_tf32(r[i].y); r[i].z = to_tf32(r[i].z); r[i].w = to_tf32(r[i].w);
               }
             }
+            float *o = a.out + (p0 + warp * 32 + (lane >> 3)) * a.ldo + a.col0 + n0 + c0 + chunk * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (full || p0 + warp * 32 + 4 * i + (lane >> 3) < a.rows)
+                *reinterpret_cast<float4 *>(o + static_cast<size_t>(4 * i) * a.ldo) = r[i];
           }
           __syncwarp();
         } else {
@@ -781,8 +882,8 @@ __global__ void __launch_bounds__(kMlpThreads, OCC) mlp_layer_kernel(const __gri
       const int nb = static_cast<int>(tile - rt * n_blocks);
       const int bn = min(a.bn, a.n_pad - nb * a.bn);
       const uint32_t idesc = instr_desc_tf32(bn);
-      const unsigned buf = static_cast<unsigned>(j & 1);
-      mbar_wait(&ctl.acc_empty[buf], static_cast<unsigned>(((j >> 1) & 1) ^ 1));
+      const unsigned buf = nbuf == 2 ? static_cast<unsigned>(j & 1) : 0u;
+      mbar_wait(&ctl.acc_empty[buf], static_cast<unsigned>(((nbuf == 2 ? (j >> 1) : j) & 1) ^ 1));
       tc_fence_after();
       const uint32_t acc = tmem + buf * static_cast<uint32_t>(a.tmem_cols);
       for (int kc = 0; kc < kc_total; ++kc) {
@@ -794,10 +895,21 @@ __global__ void __launch_bounds__(kMlpThreads, OCC) mlp_layer_kernel(const __gri
         if (lane == 0) {
           const uint32_t sa = ring + static_cast<uint32_t>(s) * stage_bytes;
           const uint64_t adesc = smem_desc_sw128(sa), bdesc = smem_desc_sw128(sa + a_bytes);
+          if (EPI == EPI_MAXPOOL_T || EPI == EPI_STORE_T) {
+            // operands swapped: D^T[channel][row] = W . A^T, one M = 128 block of channels per accumulator of 128
+            // columns (the tile's rows); W's next 128 rows are 16 KB (>> 4 = 1024) further
+            const uint32_t idesc_t = instr_desc_tf32(kMlpBM);
+            for (int h = 0; h < bn / 128; ++h)
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4)  // K = 8 tf32 = 32 bytes per instruction: +2 in 16-byte units
-            umma_tf32(acc, adesc + static_cast<uint64_t>(k4 * 2), bdesc + static_cast<uint64_t>(k4 * 2),
-                      idesc, (kc > 0 || k4 > 0) ? 1u : 0u);
+              for (int k4 = 0; k4 < 4; ++k4)
+                umma_tf32(acc + static_cast<uint32_t>(h * 128), bdesc + static_cast<uint64_t>(h * 1024 + k4 * 2),
+                          adesc + static_cast<uint64_t>(k4 * 2), idesc_t, (kc > 0 || k4 > 0) ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4)  // K = 8 tf32 = 32 bytes per instruction: +2 in 16-byte units
+              umma_tf32(acc, adesc + static_cast<uint64_t>(k4 * 2), bdesc + static_cast<uint64_t>(k4 * 2),
+                        idesc, (kc > 0 || k4 > 0) ? 1u : 0u);
+          }
           umma_commit(&ctl.empty[s]);  // stage reusable once these MMAs have read it
           if (kc == kc_total - 1) umma_commit(&ctl.acc_full[buf]);
         }
@@ -810,7 +922,7 @@ __global__ void __launch_bounds__(kMlpThreads, OCC) mlp_layer_kernel(const __gri
   if (warp == kMlpEpiWarps + kMlpProWarps) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem),
-                 "r"(static_cast<uint32_t>(2 * a.tmem_cols))
+                 "r"(nbuf * static_cast<uint32_t>(a.tmem_cols))
                  : "memory");
   }
 }
@@ -830,25 +942,44 @@ int launch_mlp(MlpArgs &a, cudaStream_t st) {
   const size_t stage_bytes = kMlpBM * 128 + align_up(static_cast<size_t>(a.bn) * 128, 1024);
   const int sms = std::max(1, sm_count() - a.reserve_sms);
   const long long tiles = ((a.rows + kMlpBM - 1) / kMlpBM) * ceil_div(a.n_pad, a.bn);
-  // two CTAs per SM when both fit: accumulators 2 x 2 x tmem_cols <= 512 columns, >= 3 stages in half the
-  // shared memory, and enough tiles to feed twice the CTAs (PVN3D_MLP_OCC=1 forces one)
+  // two CTAs per SM when both fit: accumulators <= 512 TMEM columns in total (2 x 2 x <=128, or 2 x 1 x 256: wide
+  // tiles give up the second accumulator of the CTA, the co-resident CTA fills the gap), >= min_stages stages in
+  // half the shared memory, and enough tiles to feed twice the CTAs (PVN3D_MLP_OCC=1 forces one CTA per SM,
+  // PVN3D_MLP_ACC1=0 keeps wide tiles at one CTA per SM, PVN3D_MLP_OCC2_TILES = tiles-per-SM threshold)
   static const int occ_env = [] { const char *e = getenv("PVN3D_MLP_OCC"); return e ? atoi(e) : 0; }();
-  const size_t budget2 = (92 * 1024);   // ring of one of two co-resident CTAs (+17 KB control and staging each)
+  static const int acc1_env = [] { const char *e = getenv("PVN3D_MLP_ACC1"); return e ? atoi(e) : 1; }();
+  static const int tiles_env = [] { const char *e = getenv("PVN3D_MLP_OCC2_TILES"); return e ? atoi(e) : 4; }();
+  static const int budget_env = [] { const char *e = getenv("PVN3D_MLP_OCC2_KB"); return e ? atoi(e) : 96; }();
+  const size_t budget2 = static_cast<size_t>(std::min(std::max(budget_env, 48), 96)) * 1024;   // ring of one of two co-resident CTAs
   // asynchronous producers (pre-rounded dense activations) keep two chunks in flight: >= 3 stages
   const size_t min_stages = ((PRO == PRO_DENSE || PRO == PRO_SA_GATHER) && a.a_tf32) ? 3 : 2;
-  bool occ2 = a.tmem_cols <= 128 && min_stages * stage_bytes <= budget2 && tiles >= 4ll * sms;
-  if (occ_env == 1) occ2 = false;
+  // ... and at two CTAs per SM a ring of only three stages starves them unless a tile is a single chunk (measured:
+  // 96 -> 128 max-pool layer 154 us with 6 stages at one CTA per SM, 213 us with 3 stages at two)
+  const size_t min_stages2 = (min_stages == 3 && a.k_pad > 32) ? 4 : min_stages;
+  const bool fits2 = min_stages2 * stage_bytes <= budget2 && tiles >= static_cast<long long>(tiles_env) * sms;
+  bool occ2 = a.tmem_cols <= 128 && fits2;
+  a.acc_bufs = 2;
+  if (!occ2 && a.tmem_cols == 256 && fits2 && acc1_env) {
+    occ2 = true;
+    a.acc_bufs = 1;
+  }
+  if (occ_env == 1) {
+    occ2 = false;
+    a.acc_bufs = 2;
+  }
   int stages = static_cast<int>((occ2 ? budget2 : size_t(208 * 1024)) / stage_bytes);
   if (stages > kMlpMaxStages) stages = kMlpMaxStages;
   if (stages < 2) stages = 2;
   a.stages = stages;
-  const size_t smem = stages * stage_bytes + 1024 + kMlpEpiWarps * 4096;  // ring + epilogue staging
+  const size_t smem = stages * stage_bytes + kMlpEpiWarps * 4096 + 256;  // ring + epilogue staging + barriers
+  static_assert(sizeof(MlpSmemCtl) <= 256, "barrier block");
   a.use_tma = weight_tensor_map(&a.tmap, a.w, a.k_pad, a.n_pad, a.bn) ? 1 : 0;
   if (occ2) {
     auto kern = mlp_layer_kernel<PRO, EPI, 2>;
     static PerDeviceOnce once2;
     PVN3D_ONCE_PER_DEVICE(once2,
-                          cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024),
+                          (cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100),
+                           cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 113 * 1024)),
                           "mlp smem attr (2 CTAs/SM)");
     const unsigned grid = static_cast<unsigned>(std::min<long long>(tiles, 2ll * sms));
     kern<<<grid, kMlpThreads, smem, st>>>(a);
@@ -1361,6 +1492,15 @@ int dispatch(MlpArgs &a, int pro, int pool, cudaStream_t st) {
   if (pool) {
     if (pool != 8 && pool != 16 && pool != 32) return PVN3D_ERR_UNSUPPORTED;
     a.pool = pool;
+    // 128-channel pooled layers: transposed accumulator, register max instead of shuffles (79 -> 51 us and 154 -> 125 us
+    // on the SA2 scales).  Tiles of 256 channels work too (PVN3D_MLP_POOLT=2) but measured 5-25 % SLOWER: two
+    // M=128 x N=128 TF32 MMAs per K step read 128 B of shared memory per clock, the N=256 form 96.  PVN3D_MLP_POOLT=0:
+    // the shuffle epilogue everywhere.
+    static const int poolt_env = [] { const char *e = getenv("PVN3D_MLP_POOLT"); return e ? atoi(e) : 1; }();
+    const bool t128 = a.n_pad == 128;
+    const bool t256 = a.n_pad % 128 == 0 && (a.n_pad <= 256 || a.n_pad % 256 == 0);
+    if (pro == PRO_DENSE && ((poolt_env == 1 && t128) || (poolt_env == 2 && t256)))
+      return launch_mlp<PRO_DENSE, EPI_MAXPOOL_T>(a, st);
     if (pro == PRO_DENSE) return launch_mlp<PRO_DENSE, EPI_MAXPOOL>(a, st);
     if (pro == PRO_SA_GATHER) return launch_mlp<PRO_SA_GATHER, EPI_MAXPOOL>(a, st);
     if (pro == PRO_SA_FACT) return launch_mlp<PRO_SA_FACT, EPI_MAXPOOL>(a, st);
@@ -1380,21 +1520,28 @@ int dispatch(MlpArgs &a, int pro, int pool, cudaStream_t st) {
 // ~1 m and their DIFFERENCES ~1 cm: a single TF32 rounding of x would cost 10 % of the difference)
 __global__ void sa_factor_table_kernel(const float *__restrict__ xyz, const float *__restrict__ feat, int ldf,
                                        int c_feat, long long rows, int k_pad, float *__restrict__ out) {
-  const long long p = static_cast<long long>(blockIdx.x) * blockDim.y + threadIdx.y;
+  // one 16-byte group of a row per thread (k_pad / 4 threads per row): 128-byte stores, 4+ rows per warp
+  const int qpr = k_pad >> 2;
+  const long long g = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long p = g / qpr;
   if (p >= rows) return;
-  float *o = out + p * k_pad;
-  for (int c = threadIdx.x; c < k_pad; c += blockDim.x) {
-    float v = 0.f;
+  const int c0 = static_cast<int>(g - p * qpr) * 4;
+  float v[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int c = c0 + e;
+    float r = 0.f;
     if (c < c_feat) {
-      v = to_tf32(__ldg(feat + p * ldf + c));
+      r = to_tf32(__ldg(feat + p * ldf + c));
     } else if (c < c_feat + 6) {
       const int d = (c - c_feat) % 3;
       const float x = __ldg(xyz + p * 3 + d);
       const float hi = to_tf32(x);
-      v = c < c_feat + 3 ? hi : to_tf32(x - hi);
+      r = c < c_feat + 3 ? hi : to_tf32(x - hi);
     }
-    o[c] = v;
+    v[e] = r;
   }
+  *reinterpret_cast<float4 *>(out + p * k_pad + c0) = make_float4(v[0], v[1], v[2], v[3]);
 }
 // V[i, n] = sum_d Wx[n, d] * c_i[d] - bias[n]   (fp32 FMAs; Wx = the TF32-rounded xyz columns of W1)
 __global__ void sa_centre_term_kernel(const float *__restrict__ centres, const float *__restrict__ wx,
@@ -1561,9 +1708,10 @@ extern "C" int pvn3d_sa_factor_table(const float *xyz, const float *feat_pm, int
       k_pad % 32)
     return PVN3D_ERR_INVALID_ARG;
   if (rows == 0) return PVN3D_OK;
-  const dim3 block(32, 8);
-  sa_factor_table_kernel<<<static_cast<unsigned>((rows + 7) / 8), block, 0, as_stream(stream)>>>(xyz, feat_pm, ldf, c_feat,
-                                                                                                rows, k_pad, out);
+  const long long groups = rows * (k_pad / 4);
+  if ((groups + 255) / 256 > 0x7fffffffll || (reinterpret_cast<uintptr_t>(out) & 15u)) return PVN3D_ERR_UNSUPPORTED;
+  sa_factor_table_kernel<<<static_cast<unsigned>((groups + 255) / 256), 256, 0, as_stream(stream)>>>(xyz, feat_pm, ldf, c_feat,
+                                                                                                    rows, k_pad, out);
   return check_launch("sa_factor_table_kernel");
 }
 
@@ -1614,6 +1762,13 @@ extern "C" int pvn3d_mlp_fp_fact(const float *p, const float *s, int ld, int c_v
   a.out = out; a.ldo = ldo; a.col0 = col0;
   a.relu = flags & PVN3D_MLP_RELU; a.round_out = (flags & PVN3D_MLP_ROUND_OUT) ? 1 : 0;
   a.reserve_sms = (flags >> 8) & 0xff;
+  if (flags & PVN3D_MLP_OUT_CN) {
+    // out = [b][n_pad][n_unknown]: one or two 128-channel accumulators per tile, 32-point groups inside a frame
+    if ((n_pad != 128 && n_pad != 256) || n_unknown % 32 || (reinterpret_cast<uintptr_t>(out) & 15u))
+      return PVN3D_ERR_UNSUPPORTED;
+    a.out_cn = n_unknown; a.pool = 0; a.ldo = n_pad; a.col0 = 0;
+    return launch_mlp<PRO_FP_FACT, EPI_STORE_T>(a, as_stream(stream));
+  }
   return dispatch(a, PRO_FP_FACT, 0, as_stream(stream));
 }
 

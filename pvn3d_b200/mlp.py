@@ -64,7 +64,7 @@ class PackedLayer:
         self.bias[:n] = bias
 
 
-MLP_RELU, MLP_ROUND_OUT, MLP_A_TF32 = 1, 2, 4      # include/pvn3d_b200.h PVN3D_MLP_*
+MLP_RELU, MLP_ROUND_OUT, MLP_A_TF32, MLP_OUT_CN = 1, 2, 4, 16      # include/pvn3d_b200.h PVN3D_MLP_*
 
 
 def _flags(relu, round_out=False, a_tf32=False, reserve=0):
@@ -163,16 +163,19 @@ def mlp_sa_fact(u: torch.Tensor, v: torch.Tensor, idx: torch.Tensor, n: int, lay
 
 
 def mlp_fp_fact(p: torch.Tensor, s_: torch.Tensor, nn_idx: torch.Tensor, nn_w: torch.Tensor, m_known: int,
-                layer: PackedLayer, relu=True, round_out=False, reserve=0):
-    """second layer of a factored FP module: rows relu(sum_t w_t P[idx_t] + S) -> layer (pvn3d_mlp_fp_fact)"""
+                layer: PackedLayer, relu=True, round_out=False, reserve=0, out_cn=False):
+    """second layer of a factored FP module: rows relu(sum_t w_t P[idx_t] + S) -> layer (pvn3d_mlp_fp_fact).
+    out_cn: return [b, n_pad, n_unknown] (channel-major frames, PVN3D_MLP_OUT_CN) instead of [b * n_unknown, n_pad]"""
     lib = _lib.load()
     b, n_unknown = nn_idx.shape[0], nn_idx.shape[1]
     ld = p.size(-1)
-    out = torch.empty((b * n_unknown, layer.n_pad), dtype=torch.float32, device=p.device)
+    shape = (b, layer.n_pad, n_unknown) if out_cn else (b * n_unknown, layer.n_pad)
+    out = torch.empty(shape, dtype=torch.float32, device=p.device)
     with torch.cuda.device(p.device):
         rc = lib.pvn3d_mlp_fp_fact(ptr(p), ptr(s_), ld, ld, ptr(nn_idx), ptr(nn_w), b, n_unknown, m_known, ptr(layer.w),
-                                   ptr(layer.bias), layer.k_pad, layer.n_pad, _flags(relu, round_out, reserve=reserve),
-                                   ptr(out), out.size(-1), 0, _stream(p.device))
+                                   ptr(layer.bias), layer.k_pad, layer.n_pad,
+                                   _flags(relu, round_out, reserve=reserve) | (MLP_OUT_CN if out_cn else 0),
+                                   ptr(out), layer.n_pad, 0, _stream(p.device))
     check(rc, "pvn3d_mlp_fp_fact")
     return out
 
@@ -411,12 +414,15 @@ class FusedPointnet2MSG:
         return self.queries(self.sampling(pointcloud, fps_chunk))
 
     @torch.no_grad()
-    def features(self, pointcloud: torch.Tensor, plan: "GeoPlan", reserve_sms: int = 0) -> torch.Tensor:
+    def features(self, pointcloud: torch.Tensor, plan: "GeoPlan", reserve_sms: int = 0, reserve_levels: int = 5) -> torch.Tensor:
         """The shared MLPs of all SA / FP levels on a geometry plan -> [B,128,N].  reserve_sms: SMs the persistent
-        MLP kernels leave free for kernels of other streams (the next batch's sampling)."""
+        MLP kernels leave free for kernels of other streams (the next batch's sampling); reserve_levels: the SA levels
+        0 .. reserve_levels-1 do so (5: the FP modules too) -- the sampling of the next batch is over well before the
+        MLPs are, and the later layers then take the whole machine."""
         b, n0, width = pointcloud.shape
         c0 = width - 3
-        rs = int(reserve_sms)
+        rs_all = int(reserve_sms)
+        rs = rs_all if reserve_levels > 0 else 0
         if not plan.ball:
             self.queries(plan)
         # level-0 descriptors are columns 3.. of the input rows themselves (point-major already)
@@ -425,6 +431,7 @@ class FusedPointnet2MSG:
         l_xyz = plan.l_xyz
         table0 = None
         for li, (npoint, radii, nsamples, _) in enumerate(SA_SPEC):
+            rs = rs_all if li < reserve_levels else 0
             x, new_xyz = l_xyz[li], l_xyz[li + 1]
             fptr, ldf, c_feat = feats[-1]
             out_l = torch.empty((b, npoint, self.sa_out[li]), dtype=torch.float32, device=self.dev)
@@ -471,6 +478,7 @@ class FusedPointnet2MSG:
             keep.append(out_l)
         # feature propagation, deepest first (pvn3d.py:149-152)
         l_feat = list(keep)            # l_feat[i]: tensor owning level i's descriptors (point-major)
+        rs = rs_all if reserve_levels >= 5 else 0
         for i in range(3, -1, -1):
             unknown, known = l_xyz[i], l_xyz[i + 1]
             nn_idx, nn_w = plan.nn[i]
@@ -488,7 +496,12 @@ class FusedPointnet2MSG:
                 pk = mlp_dense(kf2d, lk, relu=False, reserve=rs)                                   # once per known point
                 skip2d = table0 if i == 0 else keep[i].view(-1, keep[i].size(-1))
                 sk = mlp_dense(skip2d, ls, relu=False, reserve=rs, a_tf32=(i == 0) or self.round_tables)
-                h = mlp_fp_fact(pk, sk, nn_idx, nn_w, known.size(1), layers[1], round_out=False, reserve=rs)
+                # the module's output IS the network's: written channel-major ([B,128,N]) straight from the accumulator
+                cn = layers[1].n_pad in (128, 256) and layers[1].n == layers[1].n_pad and unknown.size(1) % 32 == 0
+                h = mlp_fp_fact(pk, sk, nn_idx, nn_w, known.size(1), layers[1], round_out=False, reserve=rs, out_cn=cn)
+                if cn:
+                    self._m("mlp")
+                    return h
             elif self.chain:
                 h = mlp_fp_chain(known_feat, nn_idx, nn_w, sptr, lds, c1, self.fp_chain[i], reserve=rs)
             else:

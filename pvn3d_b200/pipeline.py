@@ -12,6 +12,8 @@ from __future__ import annotations
 
 from typing import Dict, Optional
 
+import os
+
 import numpy as np
 import torch
 
@@ -25,7 +27,8 @@ class FramePipeline:
     def __init__(self, shape: str, batch: int, n_points: int = fixtures.N_SAMPLE_POINTS, device="cuda",
                  lm_obj_id: int = 1, early_exit: bool = False, model: Optional[torch.nn.Module] = None,
                  allow_tf32: bool = True, engine: str = "fused", ms_mode: Optional[str] = None,
-                 overlap: bool = True, bandwidth: float = 0.08, fps_chunk: int = 16, pose_stream: bool = True):
+                 overlap: bool = True, bandwidth: float = 0.08, fps_chunk: int = 0, pose_stream: bool = True,
+                 reserve_levels: Optional[int] = None):
         self.dev = torch.device(device)
         self.shape, self.b, self.n, self.k = shape, int(batch), int(n_points), fixtures.N_KEYPOINTS
         self.model = (model if model is not None else seeded_pointnet2msg(0, 1)).to(self.dev).eval()
@@ -66,9 +69,20 @@ class FramePipeline:
         #: look-ahead: when the caller names the NEXT batch (run_device(..., next_cloud=) / run_host(hb, next_hb)),
         #: its coordinate-only half of hot path A (furthest-point sampling: 3708 dependent iterations on one CTA
         #: per frame, plus ball queries and 3-NN) runs on a third stream UNDER the shared MLPs of the current
-        #: batch.  The sampling kernels are launched `fps_chunk` frames at a time and the persistent MLP kernels
-        #: leave that many SMs free (PVN3D_MLP_RESERVE_SMS), so neither side ever waits for an SM.
-        self.fps_chunk = max(1, min(int(fps_chunk), self.b))
+        #: batch.  The sampling kernels are launched `fps_chunk` frames at a time (0: the whole batch) and the
+        #: persistent MLP kernels of the first `reserve_levels` SA levels leave that many SMs free
+        #: (PVN3D_MLP_RESERVE_SMS), so neither side waits for an SM; the sampling (2 ms for 32 frames side by side) is
+        #: over by then and the later, larger half of the MLPs takes the whole machine.  (Round 2 first used 16-frame
+        #: chunks under all layers: 2 x 2 ms of sampling -- hidden while the MLPs took 3.4 ms, the critical path once
+        #: they took 2.8.)
+        fps_chunk = int(os.environ.get("PVN3D_LA_CHUNK", fps_chunk))
+        # 32 x 12288: the MLPs (2.7 ms) outlast the sampling (2.1 ms) -> reserve under SA1-2 only (3.93 vs 4.38 ms per step
+        # with all levels reserving).  Smaller batches / larger clouds: the sampling is the critical path and a sampling
+        # kernel that finds every SM taken by a full-width layer waits for it -> reserve under every layer
+        if reserve_levels is None:
+            reserve_levels = 2 if (self.b >= 24 and self.n <= 16384) else 5
+        self.reserve_levels = int(os.environ.get("PVN3D_LA_LEVELS", reserve_levels))
+        self.fps_chunk = max(1, min(fps_chunk if fps_chunk > 0 else self.b, self.b))
         # high priority: a sampling CTA needs a whole SM (512 threads, ~56 K registers, 147 KB shared memory); when
         # an SM drains, it must win it before the thousands of small CTAs of hot path B refill it
         self._geo_stream = torch.cuda.Stream(self.dev, priority=-1) if self.overlap else None
@@ -134,8 +148,9 @@ class FramePipeline:
                     nplan.done = torch.cuda.Event()
                     nplan.done.record(g)
                 self._plan = nplan
-                reserve = min(self.fps_chunk, nc.size(0))
-            self.features = self.fused.features(cld_rgb_nrm, plan, reserve_sms=reserve)   # hot path A: [B,128,N]
+                reserve = int(os.environ.get("PVN3D_LA_RESERVE", min(self.fps_chunk, nc.size(0))))
+            self.features = self.fused.features(cld_rgb_nrm, plan, reserve_sms=reserve,
+                                                reserve_levels=self.reserve_levels)        # hot path A: [B,128,N]
         else:
             prev = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
             torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = self.allow_tf32

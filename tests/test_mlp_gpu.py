@@ -29,7 +29,11 @@ def ref_dense(a, w, b, relu, pool):
     (256, 32, 16, False, 8), (131, 48, 80, True, 0),
     # many tiles per persistent CTA (ring and both TMEM accumulators wrap), odd chunk counts, 2 column blocks
     (64000, 96, 128, True, 0), (70005, 32, 32, True, 0), (40960, 64, 64, True, 16), (9000, 544, 512, True, 0),
-    (38400, 160, 272, True, 32)])
+    (38400, 160, 272, True, 32),
+    # wide pooled layers: transposed accumulator (channel = TMEM lane), every pool size, ragged last tile, 1 / 2 / 4 column
+    # blocks, single-chunk K
+    (8192, 96, 128, True, 32), (4144, 64, 128, True, 16), (8000, 224, 256, True, 8), (50016, 224, 256, True, 32),
+    (2064, 256, 512, False, 16), (4096, 32, 1024, True, 32), (160, 384, 128, True, 16)])
 def test_dense_layer(cuda_dev, rows, k, n, relu, pool):
     g = torch.Generator().manual_seed(rows + k + n)
     a = torch.randn(rows, k, generator=g)
@@ -45,6 +49,25 @@ def test_dense_layer(cuda_dev, rows, k, n, relu, pool):
     assert (out[:, :n] - want).abs().max() <= 2e-5 * max(1.0, want.abs().max())
     if layer.n_pad > n:
         assert out[:, n:].abs().max() == 0           # pad columns are exact zeros for the next layer
+
+
+@pytest.mark.parametrize("rows,k,n,pool", [(65536, 96, 128, 32), (32768, 208, 256, 16), (8192, 384, 512, 32)])
+def test_pooled_layer_into_a_column_slice_of_the_level_table(cuda_dev, rows, k, n, pool):
+    """the call FusedPointnet2MSG makes for the last layer of an SA scale: pre-rounded activations (cp.async producers),
+    max-pool epilogue writing columns [col0, col0 + n) of a wider table, rounded output; the other columns untouched"""
+    g = torch.Generator().manual_seed(rows + n)
+    a = mlp.tf32_round(torch.randn(rows, k, generator=g)).to(cuda_dev)
+    w = torch.randn(n, k, generator=g) / np.sqrt(k)
+    b = torch.randn(n, generator=g)
+    layer = mlp.PackedLayer(w.to(cuda_dev), b.to(cuda_dev), k)
+    table = torch.full((rows // pool, n + 192), 7.0, device=cuda_dev)
+    mlp.mlp_dense(a, layer, pool=pool, out=table, col0=64, a_tf32=True, round_out=True)
+    want = mlp.tf32_round(ref_dense(a.cpu(), mlp.tf32_round(w), b, True, pool))
+    got = table.cpu()
+    assert (got[:, 64:64 + n] - want).abs().max() <= 1e-3 * max(1.0, want.abs().max())     # one TF32 ulp of the rounding
+    assert (got[:, 64:64 + n] - want).abs().mean() <= 2e-5 * max(1.0, want.abs().max())
+    assert torch.equal(got[:, 64:64 + n], mlp.tf32_round(got[:, 64:64 + n]))
+    assert (got[:, :64] == 7.0).all() and (got[:, 64 + n:] == 7.0).all()
 
 
 @pytest.mark.parametrize("rows,k,n1,n2", [(50000, 64, 96, 128), (3000, 256, 384, 512), (20000, 32, 16, 32)])
@@ -333,3 +356,27 @@ def test_factored_fp_first_layer_kernel(cuda_dev):
     want = ref_dense(mlp.tf32_round(a.reshape(-1, n1)).cpu(), l2.w.cpu()[:n2, :n1], l2.bias.cpu()[:n2], True, 0)
     # interpolation order differs in the last ulp before TF32 rounding: one TF32 ulp of the operands
     assert (got.cpu()[:, :n2] - want).abs().max() <= 1e-3 * max(1.0, float(want.abs().max()))
+
+
+@pytest.mark.parametrize("b_,n_u,m_k,n2", [(2, 1024, 333, 128), (3, 4128, 512, 256), (1, 96, 40, 128)])
+def test_factored_fp_layer_channel_major_output(cuda_dev, b_, n_u, m_k, n2):
+    """PVN3D_MLP_OUT_CN: the same numbers as the row-major call, laid out [b, n_pad, n_unknown] (what
+    Pointnet2MSG.forward returns, pvn3d.py:154) -- bit for bit, ragged last tile and frames that end inside a tile"""
+    rng = np.random.default_rng(b_ + n_u)
+    n1 = 128
+    nn = torch.from_numpy(rng.integers(0, m_k, (b_, n_u, 3)).astype(np.int32)).to(cuda_dev)
+    w = rng.uniform(0.05, 1, (b_, n_u, 3)).astype(np.float32)
+    w = torch.from_numpy(w / w.sum(-1, keepdims=True)).to(cuda_dev)
+    p = torch.from_numpy(rng.normal(size=(b_ * m_k, n1)).astype(np.float32)).to(cuda_dev)
+    s_ = torch.from_numpy(rng.normal(size=(b_ * n_u, n1)).astype(np.float32)).to(cuda_dev)
+    g = torch.Generator().manual_seed(n2)
+    l2 = mlp.PackedLayer((torch.randn(n2, n1, generator=g) / np.sqrt(n1)).to(cuda_dev), (torch.randn(n2, generator=g) * 0.1).to(cuda_dev), n1)
+    rows = mlp.mlp_fp_fact(p, s_, nn, w, m_k, l2)
+    cn = mlp.mlp_fp_fact(p, s_, nn, w, m_k, l2, out_cn=True)
+    assert cn.shape == (b_, n2, n_u)
+    assert torch.equal(cn, rows.view(b_, n_u, n2).transpose(1, 2))
+    # unsupported shapes are refused, not mis-stored
+    if n_u % 32 == 0:
+        with pytest.raises(RuntimeError):
+            mlp.mlp_fp_fact(p[:, :n1], s_, nn[:, :n_u - 1].contiguous(), w[:, :n_u - 1].contiguous(), m_k, l2, out_cn=True)
+
