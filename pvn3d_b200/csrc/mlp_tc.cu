@@ -520,8 +520,8 @@ struct MlpSmemCtl {
 // OCC = CTAs per SM the kernel is compiled for.  The layers are latency-bound (gathers through L2, TMEM
 // round trips) at 13 warps per SM; two co-resident CTAs (<= 78 registers per thread, half the operand ring,
 // two accumulators of <= 128 TMEM columns each) double the loads in flight for the narrow layers.
-template <int PRO, int EPI, int OCC, int EW>
-__global__ void __launch_bounds__((EW + kMlpProWarps + 1) * 32, OCC) mlp_layer_kernel(const __grid_constant__ MlpArgs a) {
+template <int PRO, int EPI, int OCC>
+__global__ void __launch_bounds__(kMlpThreads, OCC) mlp_layer_kernel(const __grid_constant__ MlpArgs a) {
   // dynamic shared memory only, 1024-byte aligned: [operand ring: stages x stage_bytes][epilogue staging 4 x 4 KB]
   // [barriers].  No static block and no alignment slack: two CTAs with 96 KB rings each fit one SM's 228 KB.
   extern __shared__ __align__(1024) unsigned char mlp_smem_al[];
@@ -530,7 +530,7 @@ __global__ void __launch_bounds__((EW + kMlpProWarps + 1) * 32, OCC) mlp_layer_k
   const uint32_t a_bytes = kMlpBM * 128u;
   const uint32_t stage_bytes = a_bytes + ((static_cast<uint32_t>(a.bn) * 128u + 1023u) & ~1023u);
   MlpSmemCtl &ctl = *reinterpret_cast<MlpSmemCtl *>(mlp_smem_al + static_cast<size_t>(a.stages) * stage_bytes +
-                                                    EW * 4096);
+                                                    kMlpEpiWarps * 4096);
   const unsigned nbuf = static_cast<unsigned>(a.acc_bufs);
 
   const int t = threadIdx.x;
@@ -541,7 +541,7 @@ __global__ void __launch_bounds__((EW + kMlpProWarps + 1) * 32, OCC) mlp_layer_k
   const int n_blocks = (a.n_pad + a.bn - 1) / a.bn;
   const long long total_tiles = row_tiles * n_blocks;
 
-  if (warp == EW + kMlpProWarps) {
+  if (warp == kMlpEpiWarps + kMlpProWarps) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) {
         mbar_init(&ctl.full[s], 128);
@@ -549,7 +549,7 @@ __global__ void __launch_bounds__((EW + kMlpProWarps + 1) * 32, OCC) mlp_layer_k
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(&ctl.acc_full[b], 1);
-        mbar_init(&ctl.acc_empty[b], EW * 32);
+        mbar_init(&ctl.acc_empty[b], 128);
       }
       mbar_fence_init();
     }
@@ -565,10 +565,10 @@ __global__ void __launch_bounds__((EW + kMlpProWarps + 1) * 32, OCC) mlp_layer_k
   tc_fence_after();
   const uint32_t tmem = ctl.tmem_base;
 
-  if (warp >= EW && warp < EW + kMlpProWarps) {
+  if (warp >= kMlpEpiWarps && warp < kMlpEpiWarps + kMlpProWarps) {
     // ================= producers ======================================================================
-    const int pt = (t - EW * 32) & 127;          // thread inside the group
-    const unsigned grp = (warp - EW) >> 2;       // group 0 / 1 takes even / odd chunks
+    const int pt = (t - kMlpEpiWarps * 32) & 127;          // thread inside the group
+    const unsigned grp = (warp - kMlpEpiWarps) >> 2;       // group 0 / 1 takes even / odd chunks
     const int pw = pt >> 5, sub = static_cast<int>(lane & 7u), rg = static_cast<int>(lane >> 3);
     const int r_first = 32 * pw + rg;
     bool vec_ok = true;
@@ -656,11 +656,8 @@ __global__ void __launch_bounds__((EW + kMlpProWarps + 1) * 32, OCC) mlp_layer_k
       fence_proxy_async_smem();
       mbar_arrive(&ctl.full[pend0]);
     }
-  } else if (warp < EW) {
+  } else if (warp < kMlpEpiWarps) {
     // ================= epilogue: warp w owns TMEM lanes 32w..32w+31 = rows p0+32w.. ==================
-    // EW = 8 (one CTA per SM): warps w and w + 4 share the TMEM lanes 32 (w & 3).. and take alternate 32-column blocks --
-    // the epilogue is a serial instruction stream per warp and was the bottleneck of the wide layers
-    const unsigned wq = warp & 3u;
     long long j = 0;
     for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++j) {
       const long long rt = tile / n_blocks;
@@ -671,25 +668,20 @@ __global__ void __launch_bounds__((EW + kMlpProWarps + 1) * 32, OCC) mlp_layer_k
       const unsigned buf = nbuf == 2 ? static_cast<unsigned>(j & 1) : 0u;
       mbar_wait(&ctl.acc_full[buf], static_cast<unsigned>((nbuf == 2 ? (j >> 1) : j) & 1));
       tc_fence_after();
-      const long long prow = p0 + wq * 32 + lane;
+      const long long prow = p0 + warp * 32 + lane;
       const uint32_t stg = ring + static_cast<uint32_t>(S) * stage_bytes + warp * 4096u;  // after the ring
-      const uint32_t lane_addr = tmem + buf * static_cast<uint32_t>(a.tmem_cols) + ((wq * 32u) << 16);
+      const uint32_t lane_addr = tmem + buf * static_cast<uint32_t>(a.tmem_cols) + ((warp * 32u) << 16);
       // per-frame bias (a 128-row tile never straddles batch elements: bias_npb % 128 == 0)
       const float *bias_t = a.bias + (a.bias_npb > 0 ? (p0 / a.bias_npb) * a.n_pad : 0);
-      constexpr bool kT = EPI == EPI_MAXPOOL_T || EPI == EPI_STORE_T;
-      // transposed accumulators: TMEM columns are the 128 rows of the tile, once per block of 128 channels (a tile of
-      // fewer channels still is one M = 128 MMA: the upper lanes hold nothing and their warps skip the block)
-      const int ncols = kT ? ((bn + 127) & ~127) : bn;
-      for (int c0 = 32 * static_cast<int>(warp >> 2); c0 < ncols; c0 += 32 * (EW / 4)) {
-        if (kT && (c0 & ~127) + static_cast<int>(wq) * 32 >= bn) continue;
+      for (int c0 = 0; c0 < bn; c0 += 32) {
         float v[32];
-        const int cw = kT ? 32 : min(32, bn - c0);
+        const int cw = min(32, bn - c0);
         const unsigned chunk = lane & 7u;                       // STORE: the lane's group of four columns
         const bool col_on = static_cast<int>(chunk) * 4 < cw;
         float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
         if (EPI == EPI_STORE && col_on) bq = ldg128(bias_t + n0 + c0 + chunk * 4);
         float bch = 0.f;   // MAXPOOL_T: the lane's channel = n0 + 128 * (c0 / 128) + 32 * warp + lane
-        if (EPI == EPI_MAXPOOL_T || EPI == EPI_STORE_T) bch = __ldg(bias_t + n0 + (c0 & ~127) + wq * 32 + lane);
+        if (EPI == EPI_MAXPOOL_T || EPI == EPI_STORE_T) bch = __ldg(bias_t + n0 + (c0 & ~127) + warp * 32 + lane);
         if (cw == 32) tmem_ld32(lane_addr + c0, v);
         else tmem_ld16(lane_addr + c0, v);
         if (EPI == EPI_SUMPOOL) {
@@ -706,8 +698,8 @@ __global__ void __launch_bounds__((EW + kMlpProWarps + 1) * 32, OCC) mlp_layer_k
           }
           warp_colsum_32(v, lane);
           const int col = static_cast<int>(lane);
-          if (col < cw && p0 + wq * 32 < a.rows)
-            a.out[((p0 + wq * 32) / 32) * a.ldo + a.col0 + n0 + c0 + col] = v[0];
+          if (col < cw && p0 + warp * 32 < a.rows)
+            a.out[((p0 + warp * 32) / 32) * a.ldo + a.col0 + n0 + c0 + col] = v[0];
         } else if (EPI == EPI_STORE_T) {
           // TRANSPOSED accumulator, stored channel-major: lane = channel, registers = 32 consecutive points of one
           // frame = 128 contiguous bytes of out[frame][channel][:] -- the [B, C, N] layout Pointnet2MSG.forward returns
@@ -730,7 +722,7 @@ __global__ void __launch_bounds__((EW + kMlpProWarps + 1) * 32, OCC) mlp_layer_k
           if (prow0 < a.rows) {
             const long long fb = prow0 / a.out_cn;
             const long long pt = prow0 - fb * a.out_cn;
-            const int ch0 = n0 + (c0 & ~127) + static_cast<int>(wq * 32 + (lane >> 3));
+            const int ch0 = n0 + (c0 & ~127) + static_cast<int>(warp * 32 + (lane >> 3));
             float *o = a.out + (fb * a.n_pad + ch0) * a.out_cn + pt + chunk * 4;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -746,7 +738,7 @@ __global__ void __launch_bounds__((EW + kMlpProWarps + 1) * 32, OCC) mlp_layer_k
           // shuffles -- and the 32 lanes of a warp store 32 consecutive channels of one pooled row (128 bytes).
           // Groups never straddle the end: rows % pool == 0 and 128 % pool == 0.
           const long long prow0 = p0 + (c0 & 127);          // row of register 0
-          float *o = a.out + a.col0 + n0 + (c0 & ~127) + wq * 32 + lane;
+          float *o = a.out + a.col0 + n0 + (c0 & ~127) + warp * 32 + lane;
           if (a.pool == 32) {
 #pragma unroll
             for (int w = 16; w >= 1; w >>= 1)
@@ -825,10 +817,10 @@ __global__ void __launch_bounds__((EW + kMlpProWarps + 1) * 32, OCC) mlp_layer_k
                 r[i].x = to_tf32(r[i].x); r[i].y = to_tf32(r[i].y); r[i].z = to_tf32(r[i].z); r[i].w = to_tf32(r[i].w);
               }
             }
-            float *o = a.out + (p0 + wq * 32 + (lane >> 3)) * a.ldo + a.col0 + n0 + c0 + chunk * 4;
+            float *o = a.out + (p0 + warp * 32 + (lane >> 3)) * a.ldo + a.col0 + n0 + c0 + chunk * 4;
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              if (full || p0 + wq * 32 + 4 * i + (lane >> 3) < a.rows)
+              if (full || p0 + warp * 32 + 4 * i + (lane >> 3) < a.rows)
                 *reinterpret_cast<float4 *>(o + static_cast<size_t>(4 * i) * a.ldo) = r[i];
           }
           __syncwarp();
@@ -838,11 +830,11 @@ __global__ void __launch_bounds__((EW + kMlpProWarps + 1) * 32, OCC) mlp_layer_k
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = -__int_as_float(0x7f800000);
           }
-          const long long grow0 = (p0 + wq * 32) / a.pool;  // first pooled row of this warp
+          const long long grow0 = (p0 + warp * 32) / a.pool;  // first pooled row of this warp
           if (a.pool == 32) {
             warp_colmax_32(v, lane);
             const int col = static_cast<int>(lane);
-            if (col < cw && p0 + wq * 32 < a.rows) {
+            if (col < cw && p0 + warp * 32 < a.rows) {
               float r = v[0] + __ldg(bias_t + n0 + c0 + col);
               if (a.relu) r = fmaxf(r, 0.f);
               if (a.round_out) r = to_tf32(r);
@@ -851,7 +843,7 @@ __global__ void __launch_bounds__((EW + kMlpProWarps + 1) * 32, OCC) mlp_layer_k
           } else if (a.pool == 16) {
             warp_colmax_16(v, lane);
             const int g = lane >> 4, col = static_cast<int>(lane & 15u) * 2;
-            if (col < cw && p0 + wq * 32 + g * 16 < a.rows) {
+            if (col < cw && p0 + warp * 32 + g * 16 < a.rows) {
               float2 r;
               r.x = v[0] + __ldg(bias_t + n0 + c0 + col);
               r.y = v[1] + __ldg(bias_t + n0 + c0 + col + 1);
@@ -862,7 +854,7 @@ __global__ void __launch_bounds__((EW + kMlpProWarps + 1) * 32, OCC) mlp_layer_k
           } else {  // pool == 8
             warp_colmax_8(v, lane);
             const int g = lane >> 3, col = static_cast<int>(lane & 7u) * 4;
-            if (col < cw && p0 + wq * 32 + g * 8 < a.rows) {
+            if (col < cw && p0 + warp * 32 + g * 8 < a.rows) {
               float4 r;
               r.x = v[0] + __ldg(bias_t + n0 + c0 + col);
               r.y = v[1] + __ldg(bias_t + n0 + c0 + col + 1);
@@ -907,7 +899,7 @@ __global__ void __launch_bounds__((EW + kMlpProWarps + 1) * 32, OCC) mlp_layer_k
             // operands swapped: D^T[channel][row] = W . A^T, one M = 128 block of channels per accumulator of 128
             // columns (the tile's rows); W's next 128 rows are 16 KB (>> 4 = 1024) further
             const uint32_t idesc_t = instr_desc_tf32(kMlpBM);
-            for (int h = 0; h < (bn + 127) / 128; ++h)
+            for (int h = 0; h < bn / 128; ++h)
 #pragma unroll
               for (int k4 = 0; k4 < 4; ++k4)
                 umma_tf32(acc + static_cast<uint32_t>(h * 128), bdesc + static_cast<uint64_t>(h * 1024 + k4 * 2),
@@ -927,7 +919,7 @@ __global__ void __launch_bounds__((EW + kMlpProWarps + 1) * 32, OCC) mlp_layer_k
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == EW + kMlpProWarps) {
+  if (warp == kMlpEpiWarps + kMlpProWarps) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem),
                  "r"(nbuf * static_cast<uint32_t>(a.tmem_cols))
@@ -946,7 +938,6 @@ int launch_mlp(MlpArgs &a, cudaStream_t st) {
   a.bn = ((ceil_div(a.n_pad, nblk) + 15) / 16) * 16;
   int tc = 32;
   while (tc < a.bn) tc <<= 1;
-  if ((EPI == EPI_MAXPOOL_T || EPI == EPI_STORE_T) && tc < 128) tc = 128;   // the accumulator's columns are the tile's 128 rows
   a.tmem_cols = tc;
   const size_t stage_bytes = kMlpBM * 128 + align_up(static_cast<size_t>(a.bn) * 128, 1024);
   const int sms = std::max(1, sm_count() - a.reserve_sms);
@@ -976,19 +967,15 @@ int launch_mlp(MlpArgs &a, cudaStream_t st) {
     occ2 = false;
     a.acc_bufs = 2;
   }
-  // one CTA per SM: eight epilogue warps (two per TMEM lane quadrant), 32 KB of staging tiles (PVN3D_MLP_EPI8=0: four)
-  static const int epi8_env = [] { const char *e = getenv("PVN3D_MLP_EPI8"); return e ? atoi(e) : 1; }();
-  // (not for the interpolating producers: they are producer-bound and spill at the 120 registers of 544 threads)
-  const int ew = (!occ2 && epi8_env && PRO != PRO_FP_INTERP && PRO != PRO_FP_FACT) ? 8 : 4;
-  int stages = static_cast<int>((occ2 ? budget2 : size_t((ew == 8 ? 192 : 208) * 1024)) / stage_bytes);
+  int stages = static_cast<int>((occ2 ? budget2 : size_t(208 * 1024)) / stage_bytes);
   if (stages > kMlpMaxStages) stages = kMlpMaxStages;
   if (stages < 2) stages = 2;
   a.stages = stages;
-  const size_t smem = stages * stage_bytes + ew * 4096 + 256;  // ring + epilogue staging + barriers
+  const size_t smem = stages * stage_bytes + kMlpEpiWarps * 4096 + 256;  // ring + epilogue staging + barriers
   static_assert(sizeof(MlpSmemCtl) <= 256, "barrier block");
   a.use_tma = weight_tensor_map(&a.tmap, a.w, a.k_pad, a.n_pad, a.bn) ? 1 : 0;
   if (occ2) {
-    auto kern = mlp_layer_kernel<PRO, EPI, 2, 4>;
+    auto kern = mlp_layer_kernel<PRO, EPI, 2>;
     static PerDeviceOnce once2;
     PVN3D_ONCE_PER_DEVICE(once2,
                           (cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100),
@@ -998,21 +985,12 @@ int launch_mlp(MlpArgs &a, cudaStream_t st) {
     kern<<<grid, kMlpThreads, smem, st>>>(a);
     return check_launch("mlp_layer_kernel<2>");
   }
-  const unsigned grid = static_cast<unsigned>(std::min<long long>(tiles, sms));
-  if (ew == 8) {
-    auto kern8 = mlp_layer_kernel<PRO, EPI, 1, 8>;
-    static PerDeviceOnce once8;
-    PVN3D_ONCE_PER_DEVICE(once8,
-                          cudaFuncSetAttribute(kern8, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024),
-                          "mlp smem attr (8 epilogue warps)");
-    kern8<<<grid, (8 + kMlpProWarps + 1) * 32, smem, st>>>(a);
-    return check_launch("mlp_layer_kernel<1,8>");
-  }
-  auto kern = mlp_layer_kernel<PRO, EPI, 1, 4>;
+  auto kern = mlp_layer_kernel<PRO, EPI, 1>;
   static PerDeviceOnce once;
   PVN3D_ONCE_PER_DEVICE(once,
                         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024),
                         "mlp smem attr");
+  const unsigned grid = static_cast<unsigned>(std::min<long long>(tiles, sms));
   kern<<<grid, kMlpThreads, smem, st>>>(a);
   return check_launch("mlp_layer_kernel");
 }
@@ -1519,8 +1497,7 @@ int dispatch(MlpArgs &a, int pro, int pool, cudaStream_t st) {
     // M=128 x N=128 TF32 MMAs per K step read 128 B of shared memory per clock, the N=256 form 96.  PVN3D_MLP_POOLT=0:
     // the shuffle epilogue everywhere.
     static const int poolt_env = [] { const char *e = getenv("PVN3D_MLP_POOLT"); return e ? atoi(e) : 1; }();
-    static const int poolt64_env = [] { const char *e = getenv("PVN3D_MLP_POOLT64"); return e ? atoi(e) : 1; }();
-    const bool t128 = a.n_pad == 128 || (a.n_pad == 64 && poolt64_env);   // 64 channels: M = 128 with the upper lanes idle
+    const bool t128 = a.n_pad == 128;
     const bool t256 = a.n_pad % 128 == 0 && (a.n_pad <= 256 || a.n_pad % 256 == 0);
     if (pro == PRO_DENSE && ((poolt_env == 1 && t128) || (poolt_env == 2 && t256)))
       return launch_mlp<PRO_DENSE, EPI_MAXPOOL_T>(a, st);
