@@ -563,8 +563,9 @@ def b200_arm(args, json_out):
                                          "strict": "strict: all seeds, the reference's global stop rule (reference iteration counts)",
                                          "no_freeze": "no_freeze: literal reference schedule"}[args.ms_mode],
                            "overlap": ("hot path B on its own stream under hot path A" if overlap else "single stream")
-                                      + ("; look-ahead: geometry (FPS / ball query / 3-NN) of batch i+1 on a third stream under "
-                                         "the shared MLPs of batch i" if (la and overlap) else "")},
+                                      + ("; look-ahead: furthest-point sampling of batch i+1 on a high-priority third stream under "
+                                         "the shared MLPs of batch i (whose first SA levels leave it one SM per frame)"
+                                         if (la and overlap) else "")},
                 "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": head["clocks"],
                 "frames_per_s_hbm_frac": {"value": head["value"] / world / (peak * 1e9 / FRAME_HBM_BYTES),
                                           "per_gpu_roofline_frames_per_s": peak * 1e9 / FRAME_HBM_BYTES,
